@@ -1,0 +1,125 @@
+/* libvitb200 -- C-ABI of the B200-native ViT-family forward engine.
+ *
+ * The reference (taki0112/vit-tensorflow) has NO plugin / FFI interface: its hot path sits behind plain
+ * Python classes.  The boundary preserved is the constructor + call surface
+ *     ViT(...)(img) -> logits        vit_tensorflow/vit.py:107-108,159-177
+ *     DeepViT(...)(img)              vit_tensorflow/deepvit.py:113-114,139-157
+ *     CaiT(...)(img)                 vit_tensorflow/cait.py:156-157,180-194
+ *     CrossViT(...)(img)             vit_tensorflow/cross_vit.py:233-253,290-303
+ * and this header is what the Python host classes (vit_tensorflow_b200/*.py) bind with ctypes.
+ * Plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is vb_last_error(handle)
+ *     (pass NULL for errors of vb_create / the vb_op_* helpers).  Nothing throws or aborts across the ABI.
+ *   - a handle is bound to one CUDA device and is not thread-safe; distinct handles are independent.
+ *   - weights: caller keeps ownership of host arrays, the engine copies/packs them to the device.
+ *   - images are NHWC float32 (vit.py:159, usage vit.py:193), logits float32 [batch, num_classes].
+ */
+#ifndef VITB200_H_
+#define VITB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_ABI_VERSION 1
+#if defined(__GNUC__)
+#define VB_API __attribute__((visibility("default")))
+#else
+#define VB_API
+#endif
+
+typedef struct vb_handle vb_handle;
+
+enum { VB_KIND_VIT = 0, VB_KIND_DEEPVIT = 1, VB_KIND_CAIT = 2, VB_KIND_CROSSVIT = 3 };
+enum { VB_PRECISION_FP32 = 0, VB_PRECISION_BF16 = 1 };
+enum { VB_POOL_CLS = 0, VB_POOL_MEAN = 1 };
+enum { VB_MEM_HOST = 0, VB_MEM_DEVICE = 1 };
+
+/* Constructor kwargs of the four reference classes, flattened.  Unused fields are ignored per kind. */
+typedef struct vb_config {
+  int32_t struct_size;            /* sizeof(vb_config), ABI guard */
+  int32_t kind;                   /* VB_KIND_* */
+  int32_t precision;              /* VB_PRECISION_*: FP32 = exact-fp32 SIMT path (numerics gate); BF16 = tcgen05 path */
+  int32_t image_h, image_w;       /* vit.py:133 pair(image_size) */
+  int32_t patch_h, patch_w;       /* vit.py:134 pair(patch_size) */
+  int32_t channels;               /* 3 */
+  int32_t num_classes;
+  int32_t dim, depth, heads, dim_head, mlp_dim;
+  int32_t pool;                   /* VB_POOL_* (vit.py:139,170-173) */
+  int32_t cls_depth;              /* CaiT (cait.py:156) */
+  int32_t max_batch;              /* workspace is sized for this batch */
+  /* CrossViT (cross_vit.py:233-253) */
+  int32_t sm_dim, lg_dim;
+  int32_t sm_patch_size, sm_enc_depth, sm_enc_heads, sm_enc_mlp_dim, sm_enc_dim_head;
+  int32_t lg_patch_size, lg_enc_depth, lg_enc_heads, lg_enc_mlp_dim, lg_enc_dim_head;
+  int32_t cross_attn_depth, cross_attn_heads, cross_attn_dim_head;
+  int32_t cross_depth;            /* CrossViT `depth`: number of multi-scale blocks */
+} vb_config;
+
+VB_API int vb_abi_version(void);
+
+/* Replaces <Model>.__init__ (vit.py:107-157 etc.): validates the config and allocates device state. */
+VB_API int vb_create(const vb_config* cfg, int device, vb_handle** out);
+
+/* Replaces Keras variable assignment: one call per weight, names/shapes/layouts per SURVEY.md App. B
+ * (Dense kernel [in,out], float32).  shape/ndim are checked against the config. */
+VB_API int vb_set_weight(vb_handle* h, const char* name, const float* host_data, const int64_t* shape, int32_t ndim);
+
+/* Number of weights the config expects, and the name/shape of the i-th (for the host side to enumerate). */
+VB_API int vb_num_weights(vb_handle* h);
+VB_API int vb_weight_info(vb_handle* h, int32_t index, const char** name, int64_t* shape4, int32_t* ndim);
+
+/* Packs weights for the device (bf16 K-major copies, folded constants).  Fails if a weight is missing. */
+VB_API int vb_finalize(vb_handle* h);
+
+/* Replaces <Model>.call(img) (vit.py:159-177, deepvit.py:139-157, cait.py:180-194, cross_vit.py:290-303)
+ * with inference semantics (dropout = identity).  img: NHWC float32 [batch,h,w,channels] in host or device
+ * memory (img_mem); logits: float32 [batch,num_classes] written to host or device memory (logits_mem).
+ * stream: a cudaStream_t (may be NULL = default stream).  With device buffers the call is asynchronous on
+ * `stream`; with a host logits buffer it returns after the copy completes.
+ * h, w may be smaller than the configured image (pos_embedding[:, :n+1] truncation, vit.py:165). */
+VB_API int vb_forward(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w,
+               float* logits, int32_t logits_mem, void* stream);
+
+/* Replaces model.transformer(tokens) (vit.py:99-104) for ViT / DeepViT with an arbitrary token count n,
+ * the entry the reference's wrappers use (mae.py:69, simmim.py:116, mpp.py:212).
+ * tokens/out: float32 [batch, n, dim]. */
+VB_API int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_mem, int32_t batch, int32_t n,
+                      float* out, int32_t out_mem, void* stream);
+
+/* Kernels launched by this handle's most recent forward call. */
+VB_API int64_t vb_last_launch_count(vb_handle* h);
+
+VB_API const char* vb_last_error(vb_handle* h);
+VB_API void vb_destroy(vb_handle* h);
+
+/* ---- single-operator entry points (used by the parity tests and the per-kernel benchmarks) -------------
+ * All buffers are HOST float32; bf16 variants round operands to bf16 (RNE) on the way in.
+ * *elapsed_ms (may be NULL) receives the average device time per launch over `iters` launches (CUDA events). */
+
+/* out[M,N] = epi(a[M,K] x w[K,N]): epi = (+bias[N]) -> exact-erf GELU (gelu!=0) -> (*scale[N]) -> (+res[M,N]).
+ * Any of bias/scale/res may be NULL.  precision BF16 runs the tcgen05 kernel, FP32 the SIMT kernel. */
+VB_API int vb_op_linear(int32_t precision, const float* a, const float* w, const float* bias, const float* scale,
+                 const float* res, int32_t gelu, float* out, int32_t M, int32_t N, int32_t K, int32_t iters,
+                 float* elapsed_ms);
+
+/* Multi-head attention core (vit.py:77-82): q [B,nq,h*dh], k,v [B,nk,h*dh] -> out [B,nq,h*dh];
+ * variant 0 = plain, 1 = DeepViT re-attention (mix [h,h] + LayerNorm over heads, gamma/beta [h]; deepvit.py:83-84),
+ * 2 = CaiT talking heads (mix_pre, mix_post [h,h]; cait.py:123-125). */
+VB_API int vb_op_attention(int32_t precision, int32_t variant, const float* q, const float* k, const float* v,
+                    const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta,
+                    float* out, int32_t B, int32_t nq, int32_t nk, int32_t heads, int32_t dim_head, int32_t iters,
+                    float* elapsed_ms);
+
+/* LayerNorm over the last axis, eps 1e-3 (vit.py:18): x [M,D] -> out [M,D]. */
+VB_API int vb_op_layernorm(int32_t precision, const float* x, const float* gamma, const float* beta, float* out,
+                    int32_t M, int32_t D, int32_t iters, float* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VITB200_H_ */

@@ -1,0 +1,46 @@
+"""Shared model configurations for the parity tests (small enough for the CPU oracle to finish in seconds)."""
+import numpy as np
+
+import oracle
+
+# BASELINE.json configs[0]: the numerics gate (C1).
+C1 = dict(kind="vit", image_size=224, patch_size=16, num_classes=1000, dim=192, depth=1, heads=3, mlp_dim=768)
+
+SMALL = {
+    "vit_c1": C1,
+    "vit_small": dict(kind="vit", image_size=64, patch_size=16, num_classes=10, dim=64, depth=2, heads=4, mlp_dim=128, dim_head=16),
+    "vit_mean_rect": dict(kind="vit", image_size=(48, 64), patch_size=(8, 16), num_classes=7, dim=64, depth=1, heads=2,
+                          mlp_dim=96, dim_head=32, pool="mean"),
+    "vit_noproj": dict(kind="vit", image_size=32, patch_size=8, num_classes=5, dim=64, depth=2, heads=1, mlp_dim=64, dim_head=64),
+    "deepvit_small": dict(kind="deepvit", image_size=64, patch_size=16, num_classes=10, dim=64, depth=2, heads=4, mlp_dim=128, dim_head=16),
+    "cait_small": dict(kind="cait", image_size=64, patch_size=16, num_classes=10, dim=64, depth=2, cls_depth=2, heads=4,
+                       mlp_dim=128, dim_head=16),
+    "crossvit_small": dict(kind="crossvit", image_size=64, num_classes=10, sm_dim=64, lg_dim=128, sm_patch_size=8,
+                           lg_patch_size=16, sm_enc_depth=1, lg_enc_depth=2, sm_enc_heads=2, lg_enc_heads=2,
+                           sm_enc_mlp_dim=64, lg_enc_mlp_dim=128, sm_enc_dim_head=32, lg_enc_dim_head=32,
+                           cross_attn_depth=2, cross_attn_heads=2, cross_attn_dim_head=32, depth=2),
+    "crossvit_samedim": dict(kind="crossvit", image_size=32, num_classes=6, sm_dim=64, lg_dim=64, sm_patch_size=8,
+                             lg_patch_size=16, sm_enc_depth=1, lg_enc_depth=1, sm_enc_heads=2, lg_enc_heads=2,
+                             sm_enc_mlp_dim=64, lg_enc_mlp_dim=64, sm_enc_dim_head=32, lg_enc_dim_head=32,
+                             cross_attn_depth=1, cross_attn_heads=2, cross_attn_dim_head=32, depth=1),
+}
+
+# Mid-size bf16 cases exercising the tcgen05 kernels at the real head / sequence geometry (n = 197, dh = 64).
+MID = {
+    "vit_mid": dict(kind="vit", image_size=224, patch_size=16, num_classes=1000, dim=256, depth=2, heads=4, mlp_dim=512),
+    "deepvit_mid": dict(kind="deepvit", image_size=224, patch_size=16, num_classes=100, dim=256, depth=2, heads=4, mlp_dim=512),
+    "cait_mid": dict(kind="cait", image_size=224, patch_size=16, num_classes=100, dim=192, depth=2, cls_depth=2, heads=4,
+                     mlp_dim=384, dim_head=48),
+}
+
+
+def cfg_of(name):
+    d = dict({**SMALL, **MID}[name])
+    return oracle.make_config(d.pop("kind"), **d)
+
+
+def bf16_round(x):
+    x = np.ascontiguousarray(x, np.float32)
+    u = x.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)

@@ -1,0 +1,21 @@
+// Attention entry points: the generic materialised-scores path (any shape / variant, both precisions) and the
+// tcgen05 fast path (bf16; returns false when the shape is not covered so the caller falls back to generic).
+#pragma once
+#include "common.h"
+
+namespace vb {
+
+// variant 0: softmax(QK^T*scale)V                    (vit.py:77-82, cross_vit.py:87-91)
+// variant 1: DeepViT re-attention: softmax -> head mix (mix_a [h,h]) -> LayerNorm over heads (deepvit.py:79-87)
+// variant 2: CaiT talking heads: mix_a before softmax, mix_b after (cait.py:121-127)
+template <typename T>
+void attention_generic(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, float* S, int B, int nq,
+                       int nk, int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* ln_gamma,
+                       const float* ln_beta, cudaStream_t s);
+
+template <typename T>
+bool attention_fast(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq, int nk,
+                    int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* ln_gamma,
+                    const float* ln_beta, cudaStream_t s);
+
+}  // namespace vb

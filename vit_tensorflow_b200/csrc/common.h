@@ -1,0 +1,60 @@
+// Host-side common definitions for libvitb200: error plumbing, TMA tensor-map encoding, launch interfaces
+// of the kernels (implemented in the .cu files of this directory).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+
+namespace vb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define VB_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw ::vb::Error(2, std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                               ":" + std::to_string(__LINE__) + ")");                                   \
+  } while (0)
+
+#define VB_CHECK(cond, msg)                                       \
+  do {                                                            \
+    if (!(cond)) throw ::vb::Error(1, std::string(msg));          \
+  } while (0)
+
+int sm_count();
+
+// 2-D / 3-D bf16 tensor maps (innermost dimension first), 128-byte swizzle unless swizzle == false.
+CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                         uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true);
+CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                         uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, bool swizzle128 = true);
+
+// ------------------------------------------------------------------------------------------ tcgen05 GEMM
+// out[M,N] = epilogue(A[M,K] * Wt[N,K]^T): bf16 operands (K-major), fp32 accumulation in TMEM.
+// epilogue: (+bias[n]) -> (exact-erf GELU) -> (*scale[n]) -> (+res[m,n]); out bf16.
+struct GemmBf16 {
+  CUtensorMap tmap_a, tmap_b, tmap_c;
+  int M = 0, N = 0, K = 0;
+  int block_n = 256;
+  const float* bias = nullptr;          // [N] or null
+  const float* scale = nullptr;         // [N] or null (LayerScale)
+  const __nv_bfloat16* res = nullptr;   // [M, ldr] or null (may alias out)
+  int ldr = 0;
+  bool gelu = false;
+  int grid = 0;
+};
+// lda/ldw/ldc/ldr in elements; all must be multiples of 8 (16-byte TMA strides); N % 64 == 0.
+GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt, int ldw, __nv_bfloat16* out, int ldc,
+                        int M, int N, int K, const float* bias, const float* scale, const __nv_bfloat16* res, int ldr,
+                        bool gelu);
+void gemm_bf16_run(const GemmBf16& g, cudaStream_t stream);
+bool gemm_bf16_supported(int M, int N, int K, int lda, int ldw, int ldc);
+
+}  // namespace vb

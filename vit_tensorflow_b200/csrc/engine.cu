@@ -1,0 +1,923 @@
+// libvitb200 engine: weight registry, workspace arena, forward orchestration of ViT / DeepViT / CaiT / CrossViT
+// and the extern "C" boundary declared in include/vitb200.h.
+//
+// The op sequences restate the reference's call graphs:
+//   ViT / DeepViT  vit.py:159-177, deepvit.py:139-157      CaiT  cait.py:180-194      CrossViT  cross_vit.py:290-303
+// with inference semantics (dropout = identity).  T = float runs the exact-fp32 SIMT kernels (numerics gate),
+// T = __nv_bfloat16 runs the tcgen05 GEMM / attention kernels with fp32 accumulation and statistics.
+#include "../../include/vitb200.h"
+#include "attention.cuh"
+#include "common.h"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+namespace vb {
+namespace {
+
+thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------------------------------ memory
+struct DevMem {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevMem() = default;
+  DevMem(const DevMem&) = delete;
+  DevMem& operator=(const DevMem&) = delete;
+  ~DevMem() { if (p) cudaFree(p); }
+  void ensure(size_t n) {
+    if (n <= bytes) return;
+    if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+    VB_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+};
+
+// Bump allocator over a few large device blocks; reset() per forward keeps pointers stable across calls with
+// the same shapes (so cached TMA descriptors stay valid).
+class Arena {
+ public:
+  void reset() { for (auto& b : blocks_) b.off = 0; cur_ = 0; }
+  void* alloc(size_t bytes) {
+    bytes = (bytes + 1023) & ~static_cast<size_t>(1023);
+    for (; cur_ < blocks_.size(); ++cur_) {
+      Block& b = blocks_[cur_];
+      if (b.off + bytes <= b.mem->bytes) { void* p = static_cast<char*>(b.mem->p) + b.off; b.off += bytes; return p; }
+    }
+    Block nb;
+    nb.mem.reset(new DevMem());
+    nb.mem->ensure(bytes > kBlock ? bytes : kBlock);
+    nb.off = bytes;
+    blocks_.push_back(std::move(nb));
+    cur_ = blocks_.size() - 1;
+    return blocks_.back().mem->p;
+  }
+  template <typename T> T* get(size_t count) { return static_cast<T*>(alloc(count * sizeof(T))); }
+
+ private:
+  static constexpr size_t kBlock = static_cast<size_t>(256) << 20;
+  struct Block { std::unique_ptr<DevMem> mem; size_t off = 0; };
+  std::vector<Block> blocks_;
+  size_t cur_ = 0;
+};
+
+// ------------------------------------------------------------------------------------------ weights
+struct Weight {
+  std::string name;
+  std::vector<int64_t> shape;
+  size_t count = 0;
+  float* dev = nullptr;   // fp32 copy in the Keras layout
+  bool set = false;
+};
+
+struct Linear {
+  const float* W = nullptr;      // [K, N] fp32
+  const float* bias = nullptr;   // [N] or null
+  __nv_bfloat16* Wt = nullptr;   // [N, ldw] bf16, K-major, zero padded
+  int K = 0, N = 0, ldw = 0;
+};
+struct Norm { const float* gamma = nullptr; const float* beta = nullptr; int D = 0; };
+
+struct Epi {
+  const float* bias = nullptr;
+  const float* scale = nullptr;
+  const void* res = nullptr;
+  int ldr = 0;
+  bool gelu = false;
+};
+
+struct LayerW {                    // one pre-norm transformer layer in any of the four dialects
+  Norm attn_norm, ff_norm;
+  Linear to_qkv, to_q, to_kv, to_out, fc1, fc2;
+  bool fused_qkv = false, project_out = true;
+  const float* mix_a = nullptr;    // DeepViT reattn_weights / CaiT mix_pre
+  const float* mix_b = nullptr;    // CaiT mix_post
+  Norm reattn_norm;                // DeepViT
+  const float* attn_scale = nullptr;  // CaiT LayerScale
+  const float* ff_scale = nullptr;
+  int heads = 0, dim_head = 0, variant = 0;
+};
+
+struct EmbedW { Linear patch; const float* pos = nullptr; const float* cls = nullptr; int dim = 0, n_pos = 0; };
+struct CrossW { bool proj = false; Linear project_in, project_out, to_q, to_kv, to_out; Norm norm; };
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+}  // namespace vb
+
+using namespace vb;
+
+struct vb_handle {
+  vb_config cfg;
+  int device = 0;
+  bool finalized = false;
+  std::string error;
+  std::vector<Weight> weights;
+  std::map<std::string, int> windex;
+  std::vector<std::unique_ptr<DevMem>> owned;
+  Arena arena;
+  DevMem img_dev, logits_dev, tok_dev;
+  long long last_launches = 0;
+
+  // model structure (filled by finalize)
+  EmbedW embed, sm_embed, lg_embed;
+  std::vector<LayerW> layers, cls_layers;
+  struct XBlock { std::vector<LayerW> sm_layers, lg_layers; Norm sm_final, lg_final; std::vector<CrossW> sm_attend_lg, lg_attend_sm; };
+  std::vector<XBlock> xblocks;
+  Norm head_norm, sm_head_norm, lg_head_norm;
+  Linear head, sm_head, lg_head;
+
+  // cached patch-embedding residual terms, keyed by (embed ptr, batch, rows)
+  struct ResKey { const void* e; int B, rows; bool operator<(const ResKey& o) const { return std::tie(e, B, rows) < std::tie(o.e, o.B, o.rows); } };
+  std::map<ResKey, std::unique_ptr<DevMem>> embed_res;
+
+  // cached tcgen05 GEMM plans (TMA descriptors)
+  using PlanKey = std::tuple<const void*, int, const void*, const void*, int, int, int, int, const void*, const void*, const void*, int, bool>;
+  std::map<PlanKey, GemmBf16> plans;
+
+  bool bf16() const { return cfg.precision == VB_PRECISION_BF16; }
+
+  // ---------------------------------------------------------------- weight registry
+  void expect(const std::string& name, std::vector<int64_t> shape) {
+    Weight w;
+    w.name = name;
+    w.shape = std::move(shape);
+    w.count = 1;
+    for (auto d : w.shape) w.count *= static_cast<size_t>(d);
+    windex[name] = static_cast<int>(weights.size());
+    weights.push_back(std::move(w));
+  }
+  void expect_dense(const std::string& n, int din, int dout, bool bias = true) {
+    expect(n + ".kernel", {din, dout});
+    if (bias) expect(n + ".bias", {dout});
+  }
+  void expect_ln(const std::string& n, int d) { expect(n + ".gamma", {d}); expect(n + ".beta", {d}); }
+  void expect_layer(const std::string& pre, int dim, int heads, int dh, int mlp, int kind) {
+    const int inner = heads * dh;
+    expect_ln(pre + "attn_norm", dim);
+    if (kind == VB_KIND_VIT || kind == VB_KIND_DEEPVIT) expect_dense(pre + "to_qkv", dim, 3 * inner, false);
+    else { expect_dense(pre + "to_q", dim, inner, false); expect_dense(pre + "to_kv", dim, 2 * inner, false); }
+    if (kind == VB_KIND_DEEPVIT) { expect(pre + "reattn_weights", {heads, heads}); expect_ln(pre + "reattn_norm", heads); }
+    if (kind == VB_KIND_CAIT) { expect(pre + "mix_pre", {heads, heads}); expect(pre + "mix_post", {heads, heads}); }
+    const bool po = !(kind == VB_KIND_VIT && heads == 1 && dh == dim);   // vit.py:53
+    if (po) expect_dense(pre + "to_out", inner, dim);
+    expect_ln(pre + "ff_norm", dim);
+    expect_dense(pre + "fc1", dim, mlp);
+    expect_dense(pre + "fc2", mlp, dim);
+  }
+  void build_expected() {
+    const vb_config& c = cfg;
+    const int C = c.channels;
+    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT) {
+      const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
+      expect("pos_embedding", {1, np + 1, c.dim});
+      expect("cls_token", {1, 1, c.dim});
+      expect_dense("patch", c.patch_h * c.patch_w * C, c.dim);
+      for (int L = 0; L < c.depth; ++L) expect_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind);
+      expect_ln("head_norm", c.dim);
+      expect_dense("head", c.dim, c.num_classes);
+    } else if (c.kind == VB_KIND_CAIT) {
+      const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
+      expect("pos_embedding", {1, np, c.dim});
+      expect("cls_token", {1, 1, c.dim});
+      expect_dense("patch", c.patch_h * c.patch_w * C, c.dim);
+      for (int st = 0; st < 2; ++st) {
+        const std::string stack = st == 0 ? "patch_transformer" : "cls_transformer";
+        const int depth = st == 0 ? c.depth : c.cls_depth;
+        for (int L = 0; L < depth; ++L) {
+          const std::string pre = stack + ".layers." + std::to_string(L) + ".";
+          expect(pre + "attn_scale", {1, 1, c.dim});
+          expect(pre + "ff_scale", {1, 1, c.dim});
+          expect_layer(pre, c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT);
+        }
+      }
+      expect_ln("head_norm", c.dim);
+      expect_dense("head", c.dim, c.num_classes);
+    } else {
+      for (int b = 0; b < 2; ++b) {
+        const std::string br = b == 0 ? "sm" : "lg";
+        const int dim = b == 0 ? c.sm_dim : c.lg_dim, p = b == 0 ? c.sm_patch_size : c.lg_patch_size;
+        const int np = (c.image_h / p) * (c.image_w / p);
+        expect_dense(br + "_embed.patch", p * p * C, dim);
+        expect(br + "_embed.pos_embedding", {1, np + 1, dim});
+        expect(br + "_embed.cls_token", {1, 1, dim});
+      }
+      const int xinner = c.cross_attn_heads * c.cross_attn_dim_head;
+      for (int D = 0; D < c.cross_depth; ++D) {
+        const std::string bp = "blocks." + std::to_string(D) + ".";
+        for (int b = 0; b < 2; ++b) {
+          const std::string br = b == 0 ? "sm" : "lg";
+          const int dim = b == 0 ? c.sm_dim : c.lg_dim;
+          const int depth = b == 0 ? c.sm_enc_depth : c.lg_enc_depth, heads = b == 0 ? c.sm_enc_heads : c.lg_enc_heads;
+          const int dh = b == 0 ? c.sm_enc_dim_head : c.lg_enc_dim_head, mlp = b == 0 ? c.sm_enc_mlp_dim : c.lg_enc_mlp_dim;
+          for (int L = 0; L < depth; ++L) expect_layer(bp + br + "_enc.layers." + std::to_string(L) + ".", dim, heads, dh, mlp, VB_KIND_CROSSVIT);
+          expect_ln(bp + br + "_enc.final_norm", dim);
+        }
+        for (int R = 0; R < c.cross_attn_depth; ++R) {
+          for (int b = 0; b < 2; ++b) {
+            const std::string n = bp + "cross." + std::to_string(R) + (b == 0 ? ".sm_attend_lg." : ".lg_attend_sm.");
+            const int din = b == 0 ? c.sm_dim : c.lg_dim, dout = b == 0 ? c.lg_dim : c.sm_dim;
+            if (din != dout) { expect_dense(n + "project_in", din, dout); expect_dense(n + "project_out", dout, din); }
+            expect_ln(n + "norm", dout);
+            expect_dense(n + "to_q", dout, xinner, false);
+            expect_dense(n + "to_kv", dout, 2 * xinner, false);
+            expect_dense(n + "to_out", xinner, dout);
+          }
+        }
+      }
+      expect_ln("sm_head_norm", c.sm_dim); expect_dense("sm_head", c.sm_dim, c.num_classes);
+      expect_ln("lg_head_norm", c.lg_dim); expect_dense("lg_head", c.lg_dim, c.num_classes);
+    }
+  }
+
+  const float* W(const std::string& name) const {
+    auto it = windex.find(name);
+    VB_CHECK(it != windex.end(), "internal: unknown weight " + name);
+    return weights[it->second].dev;
+  }
+  bool has(const std::string& name) const { return windex.count(name) != 0; }
+
+  Linear make_linear(const std::string& n, int K, int N, bool bias = true) {
+    Linear L;
+    L.W = W(n + ".kernel");
+    L.bias = bias ? W(n + ".bias") : nullptr;
+    L.K = K; L.N = N; L.ldw = round_up(K, 8);
+    if (bf16()) {
+      owned.emplace_back(new DevMem());
+      owned.back()->ensure(static_cast<size_t>(N) * L.ldw * sizeof(__nv_bfloat16));
+      L.Wt = static_cast<__nv_bfloat16*>(owned.back()->p);
+      pack_weight_bf16(L.W, L.Wt, K, N, L.ldw, 0);
+    }
+    return L;
+  }
+  Norm make_norm(const std::string& n, int D) { return Norm{W(n + ".gamma"), W(n + ".beta"), D}; }
+  LayerW make_layer(const std::string& pre, int dim, int heads, int dh, int mlp, int kind) {
+    LayerW l;
+    const int inner = heads * dh;
+    l.heads = heads; l.dim_head = dh;
+    l.attn_norm = make_norm(pre + "attn_norm", dim);
+    l.ff_norm = make_norm(pre + "ff_norm", dim);
+    if (kind == VB_KIND_VIT || kind == VB_KIND_DEEPVIT) { l.fused_qkv = true; l.to_qkv = make_linear(pre + "to_qkv", dim, 3 * inner, false); }
+    else { l.to_q = make_linear(pre + "to_q", dim, inner, false); l.to_kv = make_linear(pre + "to_kv", dim, 2 * inner, false); }
+    if (kind == VB_KIND_DEEPVIT) { l.variant = 1; l.mix_a = W(pre + "reattn_weights"); l.reattn_norm = make_norm(pre + "reattn_norm", heads); }
+    if (kind == VB_KIND_CAIT) {
+      l.variant = 2; l.mix_a = W(pre + "mix_pre"); l.mix_b = W(pre + "mix_post");
+      l.attn_scale = W(pre + "attn_scale"); l.ff_scale = W(pre + "ff_scale");
+    }
+    l.project_out = has(pre + "to_out.kernel");
+    if (l.project_out) l.to_out = make_linear(pre + "to_out", inner, dim);
+    l.fc1 = make_linear(pre + "fc1", dim, mlp);
+    l.fc2 = make_linear(pre + "fc2", mlp, dim);
+    return l;
+  }
+  EmbedW make_embed(const std::string& pre, int p_h, int p_w, int dim, int n_pos) {
+    EmbedW e;
+    e.patch = make_linear(pre + "patch", p_h * p_w * cfg.channels, dim);
+    e.pos = W(pre + "pos_embedding");
+    e.cls = has(pre + "cls_token") ? W(pre + "cls_token") : nullptr;
+    e.dim = dim; e.n_pos = n_pos;
+    return e;
+  }
+
+  void finalize() {
+    for (auto& w : weights) VB_CHECK(w.set, "vb_finalize: weight '" + w.name + "' was never set");
+    VB_CUDA(cudaSetDevice(device));
+    owned.clear(); layers.clear(); cls_layers.clear(); xblocks.clear(); plans.clear(); embed_res.clear();
+    const vb_config& c = cfg;
+    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT) {
+      const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
+      embed = make_embed("", c.patch_h, c.patch_w, c.dim, np + 1);
+      for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind));
+      head_norm = make_norm("head_norm", c.dim);
+      head = make_linear_f32("head", c.dim, c.num_classes);
+    } else if (c.kind == VB_KIND_CAIT) {
+      const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
+      embed = make_embed("", c.patch_h, c.patch_w, c.dim, np);
+      for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("patch_transformer.layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT));
+      for (int L = 0; L < c.cls_depth; ++L) cls_layers.push_back(make_layer("cls_transformer.layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT));
+      head_norm = make_norm("head_norm", c.dim);
+      head = make_linear_f32("head", c.dim, c.num_classes);
+    } else {
+      const int nps = (c.image_h / c.sm_patch_size) * (c.image_w / c.sm_patch_size);
+      const int npl = (c.image_h / c.lg_patch_size) * (c.image_w / c.lg_patch_size);
+      sm_embed = make_embed("sm_embed.", c.sm_patch_size, c.sm_patch_size, c.sm_dim, nps + 1);
+      lg_embed = make_embed("lg_embed.", c.lg_patch_size, c.lg_patch_size, c.lg_dim, npl + 1);
+      const int xinner = c.cross_attn_heads * c.cross_attn_dim_head;
+      for (int D = 0; D < c.cross_depth; ++D) {
+        XBlock xb;
+        const std::string bp = "blocks." + std::to_string(D) + ".";
+        for (int L = 0; L < c.sm_enc_depth; ++L) xb.sm_layers.push_back(make_layer(bp + "sm_enc.layers." + std::to_string(L) + ".", c.sm_dim, c.sm_enc_heads, c.sm_enc_dim_head, c.sm_enc_mlp_dim, VB_KIND_CROSSVIT));
+        for (int L = 0; L < c.lg_enc_depth; ++L) xb.lg_layers.push_back(make_layer(bp + "lg_enc.layers." + std::to_string(L) + ".", c.lg_dim, c.lg_enc_heads, c.lg_enc_dim_head, c.lg_enc_mlp_dim, VB_KIND_CROSSVIT));
+        xb.sm_final = make_norm(bp + "sm_enc.final_norm", c.sm_dim);
+        xb.lg_final = make_norm(bp + "lg_enc.final_norm", c.lg_dim);
+        for (int R = 0; R < c.cross_attn_depth; ++R) {
+          for (int b = 0; b < 2; ++b) {
+            const std::string n = bp + "cross." + std::to_string(R) + (b == 0 ? ".sm_attend_lg." : ".lg_attend_sm.");
+            const int din = b == 0 ? c.sm_dim : c.lg_dim, dout = b == 0 ? c.lg_dim : c.sm_dim;
+            CrossW x;
+            x.proj = din != dout;
+            if (x.proj) { x.project_in = make_linear(n + "project_in", din, dout); x.project_out = make_linear(n + "project_out", dout, din); }
+            x.norm = make_norm(n + "norm", dout);
+            x.to_q = make_linear(n + "to_q", dout, xinner, false);
+            x.to_kv = make_linear(n + "to_kv", dout, 2 * xinner, false);
+            x.to_out = make_linear(n + "to_out", xinner, dout);
+            (b == 0 ? xb.sm_attend_lg : xb.lg_attend_sm).push_back(x);
+          }
+        }
+        xblocks.push_back(std::move(xb));
+      }
+      sm_head_norm = make_norm("sm_head_norm", c.sm_dim); sm_head = make_linear_f32("sm_head", c.sm_dim, c.num_classes);
+      lg_head_norm = make_norm("lg_head_norm", c.lg_dim); lg_head = make_linear_f32("lg_head", c.lg_dim, c.num_classes);
+    }
+    VB_CUDA(cudaDeviceSynchronize());
+    finalized = true;
+  }
+  Linear make_linear_f32(const std::string& n, int K, int N) {  // classifier head always runs in fp32
+    Linear L;
+    L.W = W(n + ".kernel"); L.bias = W(n + ".bias"); L.K = K; L.N = N; L.ldw = K;
+    return L;
+  }
+
+  // ---------------------------------------------------------------- ops
+  template <typename T>
+  void linear(const T* A, int lda, int M, const Linear& L, T* out, int ldc, const Epi& e, cudaStream_t s);
+
+  template <typename T>
+  void attention(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq, int nk,
+                 const LayerW& l, cudaStream_t s) {
+    attention_dispatch<T>(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, l.heads, l.dim_head, l.variant, l.mix_a, l.mix_b,
+                          l.reattn_norm.gamma, l.reattn_norm.beta, s);
+  }
+  template <typename T>
+  void attention_dispatch(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq, int nk,
+                          int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* g, const float* b,
+                          cudaStream_t s);
+
+  template <typename T>
+  const T* embed_residual(const EmbedW& e, int B, int rows, cudaStream_t s) {
+    ResKey key{&e, B, rows};
+    auto it = embed_res.find(key);
+    if (it == embed_res.end()) {
+      std::unique_ptr<DevMem> m(new DevMem());
+      m->ensure(static_cast<size_t>(B) * rows * e.dim * sizeof(T));
+      build_embed_residual<T>(static_cast<T*>(m->p), e.pos, e.cls, e.patch.bias, B, rows, e.dim, e.cls != nullptr, s);
+      it = embed_res.emplace(key, std::move(m)).first;
+    }
+    return static_cast<const T*>(it->second->p);
+  }
+
+  // patch embedding + cls token + pos embedding -> X [B*rows, dim]   (vit.py:160-165 / cait.py:181-184)
+  template <typename T>
+  T* embed_tokens(const EmbedW& e, const float* img, int B, int H, int Wd, int ph, int pw, int* rows_out, cudaStream_t s) {
+    VB_CHECK(H % ph == 0 && Wd % pw == 0, "Image dimensions must be divisible by the patch size.");
+    const int np = (H / ph) * (Wd / pw);
+    const int has_cls = e.cls != nullptr ? 1 : 0;
+    const int rows = np + has_cls;
+    VB_CHECK(rows <= e.n_pos, "image has more patches than pos_embedding rows");
+    const int Kp = bf16() ? e.patch.ldw : e.patch.K;
+    const int M = B * rows;
+    T* col = arena.get<T>(static_cast<size_t>(M) * Kp);
+    im2col<T>(img, col, B, H, Wd, cfg.channels, ph, pw, has_cls, Kp, s);
+    const T* R = embed_residual<T>(e, B, rows, s);
+    T* X = arena.get<T>(static_cast<size_t>(M) * e.dim);
+    Epi ep; ep.bias = e.patch.bias; ep.res = R; ep.ldr = e.dim;
+    Linear L = e.patch;
+    L.K = Kp;  // im2col zero-pads the patch vector to the packed weight pitch
+    linear<T>(col, Kp, M, L, X, e.dim, ep, s);
+    *rows_out = rows;
+    return X;
+  }
+
+  // one pre-norm layer, self-attention over all rows (vit.py:101-102, cait.py:150-151, cross_vit.py:109-111)
+  template <typename T>
+  void layer_self(T* X, int B, int rows, int dim, const LayerW& l, cudaStream_t s) {
+    const int M = B * rows, inner = l.heads * l.dim_head;
+    T* Y = arena.get<T>(static_cast<size_t>(M) * dim);
+    T* O = arena.get<T>(static_cast<size_t>(M) * inner);
+    layernorm<T>(X, dim, l.attn_norm.gamma, l.attn_norm.beta, Y, dim, M, dim, s);
+    if (l.fused_qkv) {
+      T* QKV = arena.get<T>(static_cast<size_t>(M) * 3 * inner);
+      linear<T>(Y, dim, M, l.to_qkv, QKV, 3 * inner, Epi(), s);
+      attention<T>(QKV, 3 * inner, QKV + inner, 3 * inner, QKV + 2 * inner, 3 * inner, O, inner, B, rows, rows, l, s);
+    } else {
+      T* Q = arena.get<T>(static_cast<size_t>(M) * inner);
+      T* KV = arena.get<T>(static_cast<size_t>(M) * 2 * inner);
+      linear<T>(Y, dim, M, l.to_q, Q, inner, Epi(), s);
+      linear<T>(Y, dim, M, l.to_kv, KV, 2 * inner, Epi(), s);
+      attention<T>(Q, inner, KV, 2 * inner, KV + inner, 2 * inner, O, inner, B, rows, rows, l, s);
+    }
+    if (l.project_out) {
+      Epi e; e.bias = l.to_out.bias; e.scale = l.attn_scale; e.res = X; e.ldr = dim;
+      linear<T>(O, inner, M, l.to_out, X, dim, e, s);
+    } else {
+      add_tokens<T>(X, O, static_cast<long long>(M) * dim, s);   // vit.py:53: identity out-projection
+    }
+    feed_forward<T>(X, M, dim, l, Y, s);
+  }
+  template <typename T>
+  void feed_forward(T* X, int M, int dim, const LayerW& l, T* Y, cudaStream_t s) {
+    T* Hb = arena.get<T>(static_cast<size_t>(M) * l.fc1.N);
+    layernorm<T>(X, dim, l.ff_norm.gamma, l.ff_norm.beta, Y, dim, M, dim, s);
+    Epi e1; e1.bias = l.fc1.bias; e1.gelu = true;
+    linear<T>(Y, dim, M, l.fc1, Hb, l.fc1.N, e1, s);
+    Epi e2; e2.bias = l.fc2.bias; e2.scale = l.ff_scale; e2.res = X; e2.ldr = dim;
+    linear<T>(Hb, l.fc1.N, M, l.fc2, X, dim, e2, s);
+  }
+  template <typename T>
+  void add_tokens(T* X, const T* O, long long count, cudaStream_t s);
+
+  // CaiT class-attention layer: x [B,1,dim] attends over [LN(x) ; patches] (cait.py:57-58,109-112,150-151)
+  template <typename T>
+  void layer_cls(T* Cx, T* ctx, int B, int nctx, int dim, const LayerW& l, cudaStream_t s) {
+    const int inner = l.heads * l.dim_head;
+    T* Yc = arena.get<T>(static_cast<size_t>(B) * dim);
+    layernorm<T>(Cx, dim, l.attn_norm.gamma, l.attn_norm.beta, Yc, dim, B, dim, s);
+    copy_tokens<T>(Yc, 1, 0, ctx, nctx, 0, 1, B, dim, s);
+    T* Q = arena.get<T>(static_cast<size_t>(B) * inner);
+    T* KV = arena.get<T>(static_cast<size_t>(B) * nctx * 2 * inner);
+    T* O = arena.get<T>(static_cast<size_t>(B) * inner);
+    linear<T>(Yc, dim, B, l.to_q, Q, inner, Epi(), s);
+    linear<T>(ctx, dim, B * nctx, l.to_kv, KV, 2 * inner, Epi(), s);
+    attention<T>(Q, inner, KV, 2 * inner, KV + inner, 2 * inner, O, inner, B, 1, nctx, l, s);
+    Epi e; e.bias = l.to_out.bias; e.scale = l.attn_scale; e.res = Cx; e.ldr = dim;
+    linear<T>(O, inner, B, l.to_out, Cx, dim, e, s);
+    feed_forward<T>(Cx, B, dim, l, Yc, s);
+  }
+
+  // CrossViT: cls [B,dcls] attends over [LN(Pin(cls)) ; other-branch patches]  (cross_vit.py:128-138,69-93,159-160)
+  template <typename T>
+  void cross_attend(T* cls, int dcls, T* ctx, int nctx, int dctx, const CrossW& x, int B, cudaStream_t s) {
+    const int heads = cfg.cross_attn_heads, dh = cfg.cross_attn_dim_head, inner = heads * dh;
+    T* xp = cls;
+    if (x.proj) {
+      xp = arena.get<T>(static_cast<size_t>(B) * dctx);
+      Epi e; e.bias = x.project_in.bias;
+      linear<T>(cls, dcls, B, x.project_in, xp, dctx, e, s);
+    }
+    T* y = arena.get<T>(static_cast<size_t>(B) * dctx);
+    layernorm<T>(xp, dctx, x.norm.gamma, x.norm.beta, y, dctx, B, dctx, s);
+    copy_tokens<T>(y, 1, 0, ctx, nctx, 0, 1, B, dctx, s);
+    T* Q = arena.get<T>(static_cast<size_t>(B) * inner);
+    T* KV = arena.get<T>(static_cast<size_t>(B) * nctx * 2 * inner);
+    T* O = arena.get<T>(static_cast<size_t>(B) * inner);
+    linear<T>(y, dctx, B, x.to_q, Q, inner, Epi(), s);
+    linear<T>(ctx, dctx, B * nctx, x.to_kv, KV, 2 * inner, Epi(), s);
+    attention_dispatch<T>(Q, inner, KV, 2 * inner, KV + inner, 2 * inner, O, inner, B, 1, nctx, heads, dh, 0, nullptr, nullptr,
+                          nullptr, nullptr, s);
+    if (x.proj) {
+      T* a = arena.get<T>(static_cast<size_t>(B) * dctx);
+      Epi e1; e1.bias = x.to_out.bias;
+      linear<T>(O, inner, B, x.to_out, a, dctx, e1, s);
+      Epi e2; e2.bias = x.project_out.bias; e2.res = cls; e2.ldr = dcls;
+      linear<T>(a, dctx, B, x.project_out, cls, dcls, e2, s);
+    } else {
+      Epi e; e.bias = x.to_out.bias; e.res = cls; e.ldr = dcls;
+      linear<T>(O, inner, B, x.to_out, cls, dcls, e, s);
+    }
+  }
+
+  template <typename T>
+  void classify(const T* X, int rows, int dim, const Norm& hn, const Linear& hd, int B, int mean_pool, float* logits,
+                bool accumulate, cudaStream_t s) {
+    float* z = arena.get<float>(static_cast<size_t>(B) * dim);
+    pool_layernorm<T>(X, rows, dim, hn.gamma, hn.beta, z, B, dim, mean_pool, s);
+    gemm_simt<float, float, float>(z, dim, hd.W, hd.N, 1, logits, hd.N, B, hd.N, dim, hd.bias, nullptr,
+                                   accumulate ? logits : nullptr, hd.N, 0, s);
+  }
+
+  template <typename T>
+  void forward_impl(const float* img, int B, int H, int Wd, float* logits, cudaStream_t s) {
+    const vb_config& c = cfg;
+    arena.reset();
+    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT) {
+      int rows = 0;
+      T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s);
+      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s);
+      classify<T>(X, rows, c.dim, head_norm, head, B, c.pool == VB_POOL_MEAN, logits, false, s);
+    } else if (c.kind == VB_KIND_CAIT) {
+      int rows = 0;
+      T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s);
+      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s);
+      T* Cx = arena.get<T>(static_cast<size_t>(B) * c.dim);
+      broadcast_row<T>(W("cls_token"), Cx, 1, B, c.dim, s);
+      T* ctx = arena.get<T>(static_cast<size_t>(B) * (rows + 1) * c.dim);
+      copy_tokens<T>(X, rows, 0, ctx, rows + 1, 1, rows, B, c.dim, s);
+      for (const auto& l : cls_layers) layer_cls<T>(Cx, ctx, B, rows + 1, c.dim, l, s);
+      classify<T>(Cx, 1, c.dim, head_norm, head, B, 0, logits, false, s);
+    } else {
+      int ns = 0, nl = 0;
+      T* S = embed_tokens<T>(sm_embed, img, B, H, Wd, c.sm_patch_size, c.sm_patch_size, &ns, s);
+      T* G = embed_tokens<T>(lg_embed, img, B, H, Wd, c.lg_patch_size, c.lg_patch_size, &nl, s);
+      T* sm_cls = arena.get<T>(static_cast<size_t>(B) * c.sm_dim);
+      T* lg_cls = arena.get<T>(static_cast<size_t>(B) * c.lg_dim);
+      T* ctx_lg = arena.get<T>(static_cast<size_t>(B) * nl * c.lg_dim);   // [LN(Pin(sm_cls)) ; lg patches]
+      T* ctx_sm = arena.get<T>(static_cast<size_t>(B) * ns * c.sm_dim);   // [LN(Pin(lg_cls)) ; sm patches]
+      for (const auto& xb : xblocks) {
+        for (const auto& l : xb.sm_layers) layer_self<T>(S, B, ns, c.sm_dim, l, s);
+        layernorm<T>(S, c.sm_dim, xb.sm_final.gamma, xb.sm_final.beta, S, c.sm_dim, B * ns, c.sm_dim, s);
+        for (const auto& l : xb.lg_layers) layer_self<T>(G, B, nl, c.lg_dim, l, s);
+        layernorm<T>(G, c.lg_dim, xb.lg_final.gamma, xb.lg_final.beta, G, c.lg_dim, B * nl, c.lg_dim, s);
+        copy_tokens<T>(S, ns, 0, sm_cls, 1, 0, 1, B, c.sm_dim, s);
+        copy_tokens<T>(G, nl, 0, lg_cls, 1, 0, 1, B, c.lg_dim, s);
+        copy_tokens<T>(G, nl, 1, ctx_lg, nl, 1, nl - 1, B, c.lg_dim, s);
+        copy_tokens<T>(S, ns, 1, ctx_sm, ns, 1, ns - 1, B, c.sm_dim, s);
+        for (size_t R = 0; R < xb.sm_attend_lg.size(); ++R) {
+          cross_attend<T>(sm_cls, c.sm_dim, ctx_lg, nl, c.lg_dim, xb.sm_attend_lg[R], B, s);
+          cross_attend<T>(lg_cls, c.lg_dim, ctx_sm, ns, c.sm_dim, xb.lg_attend_sm[R], B, s);
+        }
+        copy_tokens<T>(sm_cls, 1, 0, S, ns, 0, 1, B, c.sm_dim, s);
+        copy_tokens<T>(lg_cls, 1, 0, G, nl, 0, 1, B, c.lg_dim, s);
+      }
+      classify<T>(S, ns, c.sm_dim, sm_head_norm, sm_head, B, 0, logits, false, s);
+      classify<T>(G, nl, c.lg_dim, lg_head_norm, lg_head, B, 0, logits, true, s);
+    }
+  }
+
+  template <typename T>
+  void tokens_impl(const float* tok, int B, int n, float* out, cudaStream_t s) {
+    VB_CHECK(cfg.kind == VB_KIND_VIT || cfg.kind == VB_KIND_DEEPVIT, "vb_forward_tokens supports ViT / DeepViT");
+    arena.reset();
+    const long long count = static_cast<long long>(B) * n * cfg.dim;
+    T* X;
+    if (sizeof(T) == 4) {
+      X = reinterpret_cast<T*>(arena.get<float>(count));
+      VB_CUDA(cudaMemcpyAsync(X, tok, count * 4, cudaMemcpyDeviceToDevice, s));
+    } else {
+      X = arena.get<T>(count);
+      convert<float, __nv_bfloat16>(tok, reinterpret_cast<__nv_bfloat16*>(X), count, s);
+    }
+    for (const auto& l : layers) layer_self<T>(X, B, n, cfg.dim, l, s);
+    if (sizeof(T) == 4) VB_CUDA(cudaMemcpyAsync(out, X, count * 4, cudaMemcpyDeviceToDevice, s));
+    else convert<__nv_bfloat16, float>(reinterpret_cast<const __nv_bfloat16*>(X), out, count, s);
+  }
+};
+
+// ------------------------------------------------------------------------------------------ op dispatch
+template <>
+void vb_handle::linear<float>(const float* A, int lda, int M, const Linear& L, float* out, int ldc, const Epi& e, cudaStream_t s) {
+  gemm_simt<float, float, float>(A, lda, L.W, L.N, 1, out, ldc, M, L.N, L.K, e.bias, e.scale,
+                                 static_cast<const float*>(e.res), e.ldr, e.gelu ? 1 : 0, s);
+}
+template <>
+void vb_handle::linear<__nv_bfloat16>(const __nv_bfloat16* A, int lda, int M, const Linear& L, __nv_bfloat16* out, int ldc,
+                                      const Epi& e, cudaStream_t s) {
+  const int K = L.K;
+  const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(e.res);
+  if (gemm_bf16_supported(M, L.N, K, lda, L.ldw, ldc) && (res == nullptr || e.ldr % 8 == 0)) {
+    PlanKey key{A, lda, L.Wt, out, ldc, M, L.N, K, e.bias, e.scale, res, e.ldr, e.gelu};
+    auto it = plans.find(key);
+    if (it == plans.end())
+      it = plans.emplace(key, gemm_bf16_plan(A, lda, L.Wt, L.ldw, out, ldc, M, L.N, K, e.bias, e.scale, res, e.ldr, e.gelu)).first;
+    gemm_bf16_run(it->second, s);
+  } else {
+    gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(A, lda, L.Wt, 1, L.ldw, out, ldc, M, L.N, K, e.bias, e.scale, res,
+                                                           e.ldr, e.gelu ? 1 : 0, s);
+  }
+}
+
+template <typename T>
+void vb_handle::attention_dispatch(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq,
+                                   int nk, int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* g,
+                                   const float* b, cudaStream_t s) {
+  if (attention_fast<T>(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s)) return;
+  float* S = arena.get<float>(static_cast<size_t>(B) * heads * nq * nk);
+  attention_generic<T>(q, ldq, k, ldk, v, ldv, out, ldo, S, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s);
+}
+
+template <>
+void vb_handle::add_tokens<float>(float* X, const float* O, long long count, cudaStream_t s) { add_inplace_f32(X, O, count, s); }
+template <>
+void vb_handle::add_tokens<__nv_bfloat16>(__nv_bfloat16* X, const __nv_bfloat16* O, long long count, cudaStream_t s) {
+  // rare path (heads == 1 and dim_head == dim): go through fp32 scratch
+  float* a = arena.get<float>(count);
+  float* b = arena.get<float>(count);
+  convert<__nv_bfloat16, float>(X, a, count, s);
+  convert<__nv_bfloat16, float>(O, b, count, s);
+  add_inplace_f32(a, b, count, s);
+  convert<float, __nv_bfloat16>(a, X, count, s);
+}
+
+// ------------------------------------------------------------------------------------------ C ABI
+namespace {
+
+template <typename F>
+int guarded(vb_handle* h, F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const vb::Error& e) {
+    (h ? h->error : g_last_error) = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    (h ? h->error : g_last_error) = e.what();
+    return 3;
+  } catch (...) {
+    (h ? h->error : g_last_error) = "unknown error";
+    return 4;
+  }
+}
+
+void validate(const vb_config& c) {
+  VB_CHECK(c.struct_size == static_cast<int32_t>(sizeof(vb_config)), "vb_config.struct_size mismatch (ABI)");
+  VB_CHECK(c.kind >= VB_KIND_VIT && c.kind <= VB_KIND_CROSSVIT, "unknown model kind");
+  VB_CHECK(c.precision == VB_PRECISION_FP32 || c.precision == VB_PRECISION_BF16, "unknown precision");
+  VB_CHECK(c.channels > 0 && c.num_classes > 0 && c.image_h > 0 && c.image_w > 0, "bad image / class configuration");
+  if (c.kind == VB_KIND_CROSSVIT) {
+    VB_CHECK(c.image_h == c.image_w, "CrossViT takes a square integer image_size");
+    VB_CHECK(c.sm_patch_size > 0 && c.lg_patch_size > 0 && c.image_h % c.sm_patch_size == 0 && c.image_h % c.lg_patch_size == 0,
+             "Image dimensions must be divisible by the patch size.");
+    VB_CHECK(c.sm_dim > 0 && c.lg_dim > 0 && c.cross_depth > 0 && c.cross_attn_depth >= 0, "bad CrossViT dimensions");
+    VB_CHECK(c.sm_enc_heads <= 32 && c.lg_enc_heads <= 32 && c.cross_attn_heads <= 32, "at most 32 heads");
+  } else {
+    VB_CHECK(c.patch_h > 0 && c.patch_w > 0 && c.image_h % c.patch_h == 0 && c.image_w % c.patch_w == 0,
+             "Image dimensions must be divisible by the patch size.");
+    VB_CHECK(c.dim > 0 && c.depth >= 0 && c.heads > 0 && c.dim_head > 0 && c.mlp_dim > 0, "bad transformer dimensions");
+    VB_CHECK(c.heads <= 32, "at most 32 heads");
+    VB_CHECK(c.pool == VB_POOL_CLS || c.pool == VB_POOL_MEAN, "pool type must be either cls (cls token) or mean (mean pooling)");
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- single-operator entry points
+namespace {
+struct Timer {
+  cudaEvent_t a, b;
+  Timer() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+template <typename F>
+void timed(int iters, float* elapsed_ms, F&& f) {
+  f();  // first run produces the result (and warms up)
+  VB_CUDA(cudaDeviceSynchronize());
+  if (elapsed_ms && iters > 0) {
+    Timer t;
+    VB_CUDA(cudaEventRecord(t.a, 0));
+    for (int i = 0; i < iters; ++i) f();
+    VB_CUDA(cudaEventRecord(t.b, 0));
+    VB_CUDA(cudaEventSynchronize(t.b));
+    float ms = 0.f;
+    VB_CUDA(cudaEventElapsedTime(&ms, t.a, t.b));
+    *elapsed_ms = ms / iters;
+  }
+}
+void require_gpu() {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  VB_CHECK(e == cudaSuccess && ndev > 0, "no CUDA device available -- libvitb200 has no CPU fallback");
+}
+template <typename T>
+T* upload(DevMem& m, const float* host, size_t count) {
+  m.ensure(count * sizeof(T) + 16);
+  if (sizeof(T) == 4) {
+    VB_CUDA(cudaMemcpy(m.p, host, count * 4, cudaMemcpyHostToDevice));
+  } else {
+    DevMem tmp;
+    tmp.ensure(count * 4);
+    VB_CUDA(cudaMemcpy(tmp.p, host, count * 4, cudaMemcpyHostToDevice));
+    convert<float, __nv_bfloat16>(static_cast<const float*>(tmp.p), static_cast<__nv_bfloat16*>(m.p), static_cast<long long>(count), 0);
+    VB_CUDA(cudaDeviceSynchronize());
+  }
+  return static_cast<T*>(m.p);
+}
+template <typename T>
+void download(const T* dev, float* host, size_t count) {
+  if (sizeof(T) == 4) {
+    VB_CUDA(cudaMemcpy(host, dev, count * 4, cudaMemcpyDeviceToHost));
+  } else {
+    DevMem tmp;
+    tmp.ensure(count * 4);
+    convert<__nv_bfloat16, float>(reinterpret_cast<const __nv_bfloat16*>(dev), static_cast<float*>(tmp.p), static_cast<long long>(count), 0);
+    VB_CUDA(cudaMemcpy(host, tmp.p, count * 4, cudaMemcpyDeviceToHost));
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int vb_abi_version(void) { return VB_ABI_VERSION; }
+
+int vb_create(const vb_config* cfg, int device, vb_handle** out) {
+  return guarded(nullptr, [&] {
+    VB_CHECK(cfg != nullptr && out != nullptr, "vb_create: null argument");
+    validate(*cfg);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    VB_CHECK(e == cudaSuccess && ndev > 0, "vb_create: no CUDA device available -- libvitb200 has no CPU fallback");
+    VB_CHECK(device >= 0 && device < ndev, "vb_create: bad device index");
+    VB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    VB_CUDA(cudaGetDeviceProperties(&prop, device));
+    VB_CHECK(prop.major == 10, "vb_create: libvitb200 is built for sm_100a (Blackwell B200) only");
+    std::unique_ptr<vb_handle> h(new vb_handle());
+    h->cfg = *cfg;
+    h->device = device;
+    h->build_expected();
+    *out = h.release();
+  });
+}
+
+int vb_num_weights(vb_handle* h) { return h ? static_cast<int>(h->weights.size()) : -1; }
+
+int vb_weight_info(vb_handle* h, int32_t index, const char** name, int64_t* shape4, int32_t* ndim) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr, "null handle");
+    VB_CHECK(index >= 0 && index < static_cast<int>(h->weights.size()), "weight index out of range");
+    const Weight& w = h->weights[index];
+    if (name) *name = w.name.c_str();
+    if (ndim) *ndim = static_cast<int32_t>(w.shape.size());
+    if (shape4) for (size_t i = 0; i < w.shape.size() && i < 4; ++i) shape4[i] = w.shape[i];
+  });
+}
+
+int vb_set_weight(vb_handle* h, const char* name, const float* host_data, const int64_t* shape, int32_t ndim) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && name != nullptr && host_data != nullptr && shape != nullptr, "vb_set_weight: null argument");
+    auto it = h->windex.find(name);
+    VB_CHECK(it != h->windex.end(), std::string("vb_set_weight: this model has no weight named '") + name + "'");
+    Weight& w = h->weights[it->second];
+    bool ok = static_cast<size_t>(ndim) == w.shape.size();
+    for (int i = 0; ok && i < ndim; ++i) ok = shape[i] == w.shape[i];
+    VB_CHECK(ok, std::string("vb_set_weight: shape mismatch for '") + name + "'");
+    VB_CUDA(cudaSetDevice(h->device));
+    if (w.dev == nullptr) VB_CUDA(cudaMalloc(reinterpret_cast<void**>(&w.dev), w.count * sizeof(float)));
+    VB_CUDA(cudaMemcpy(w.dev, host_data, w.count * sizeof(float), cudaMemcpyHostToDevice));
+    w.set = true;
+    h->finalized = false;
+  });
+}
+
+int vb_finalize(vb_handle* h) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr, "null handle");
+    h->finalize();
+  });
+}
+
+int vb_forward(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w, float* logits,
+               int32_t logits_mem, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && img != nullptr && logits != nullptr, "vb_forward: null argument");
+    VB_CHECK(h->finalized, "vb_forward: call vb_finalize after setting the weights");
+    VB_CHECK(batch > 0 && img_h > 0 && img_w > 0, "vb_forward: bad batch / image size");
+    VB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long before = launch_counter();
+    const size_t img_bytes = static_cast<size_t>(batch) * img_h * img_w * h->cfg.channels * sizeof(float);
+    const size_t out_bytes = static_cast<size_t>(batch) * h->cfg.num_classes * sizeof(float);
+    const float* img_d = img;
+    if (img_mem == VB_MEM_HOST) {
+      h->img_dev.ensure(img_bytes);
+      VB_CUDA(cudaMemcpyAsync(h->img_dev.p, img, img_bytes, cudaMemcpyHostToDevice, s));
+      img_d = static_cast<const float*>(h->img_dev.p);
+    }
+    float* out_d = logits;
+    if (logits_mem == VB_MEM_HOST) {
+      h->logits_dev.ensure(out_bytes);
+      out_d = static_cast<float*>(h->logits_dev.p);
+    }
+    if (h->bf16()) h->forward_impl<__nv_bfloat16>(img_d, batch, img_h, img_w, out_d, s);
+    else h->forward_impl<float>(img_d, batch, img_h, img_w, out_d, s);
+    h->last_launches = launch_counter() - before;
+    if (logits_mem == VB_MEM_HOST) {
+      VB_CUDA(cudaMemcpyAsync(logits, out_d, out_bytes, cudaMemcpyDeviceToHost, s));
+      VB_CUDA(cudaStreamSynchronize(s));
+    }
+  });
+}
+
+int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_mem, int32_t batch, int32_t n, float* out,
+                      int32_t out_mem, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && tokens != nullptr && out != nullptr, "vb_forward_tokens: null argument");
+    VB_CHECK(h->finalized, "vb_forward_tokens: call vb_finalize after setting the weights");
+    VB_CHECK(batch > 0 && n > 0, "vb_forward_tokens: bad shape");
+    VB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long before = launch_counter();
+    const size_t bytes = static_cast<size_t>(batch) * n * h->cfg.dim * sizeof(float);
+    const float* in_d = tokens;
+    float* out_d = out;
+    if (tokens_mem == VB_MEM_HOST || out_mem == VB_MEM_HOST) h->tok_dev.ensure(2 * bytes);
+    if (tokens_mem == VB_MEM_HOST) {
+      VB_CUDA(cudaMemcpyAsync(h->tok_dev.p, tokens, bytes, cudaMemcpyHostToDevice, s));
+      in_d = static_cast<const float*>(h->tok_dev.p);
+    }
+    if (out_mem == VB_MEM_HOST) out_d = reinterpret_cast<float*>(static_cast<char*>(h->tok_dev.p) + bytes);
+    if (h->bf16()) h->tokens_impl<__nv_bfloat16>(in_d, batch, n, out_d, s);
+    else h->tokens_impl<float>(in_d, batch, n, out_d, s);
+    h->last_launches = launch_counter() - before;
+    if (out_mem == VB_MEM_HOST) {
+      VB_CUDA(cudaMemcpyAsync(out, out_d, bytes, cudaMemcpyDeviceToHost, s));
+      VB_CUDA(cudaStreamSynchronize(s));
+    }
+  });
+}
+
+int64_t vb_last_launch_count(vb_handle* h) { return h ? h->last_launches : -1; }
+
+const char* vb_last_error(vb_handle* h) { return h ? h->error.c_str() : g_last_error.c_str(); }
+
+void vb_destroy(vb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& w : h->weights) if (w.dev) cudaFree(w.dev);
+  delete h;
+}
+
+
+int vb_op_linear(int32_t precision, const float* a, const float* w, const float* bias, const float* scale, const float* res,
+                 int32_t gelu, float* out, int32_t M, int32_t N, int32_t K, int32_t iters, float* elapsed_ms) {
+  return guarded(nullptr, [&] {
+    require_gpu();
+    VB_CHECK(a && w && out && M > 0 && N > 0 && K > 0, "vb_op_linear: bad arguments");
+    DevMem dA, dW, dWt, dB, dS, dR, dO;
+    const float* db = bias ? upload<float>(dB, bias, N) : nullptr;
+    const float* ds = scale ? upload<float>(dS, scale, N) : nullptr;
+    const float* dw = upload<float>(dW, w, static_cast<size_t>(K) * N);
+    if (precision == VB_PRECISION_FP32) {
+      const float* da = upload<float>(dA, a, static_cast<size_t>(M) * K);
+      const float* dr = res ? upload<float>(dR, res, static_cast<size_t>(M) * N) : nullptr;
+      dO.ensure(static_cast<size_t>(M) * N * 4);
+      float* dout = static_cast<float*>(dO.p);
+      timed(iters, elapsed_ms, [&] { gemm_simt<float, float, float>(da, K, dw, N, 1, dout, N, M, N, K, db, ds, dr, N, gelu, 0); });
+      download<float>(dout, out, static_cast<size_t>(M) * N);
+    } else {
+      VB_CHECK(gemm_bf16_supported(M, N, K, K, K, N), "vb_op_linear(bf16): need N % 64 == 0 and K % 8 == 0");
+      const __nv_bfloat16* da = upload<__nv_bfloat16>(dA, a, static_cast<size_t>(M) * K);
+      const __nv_bfloat16* dr = res ? upload<__nv_bfloat16>(dR, res, static_cast<size_t>(M) * N) : nullptr;
+      dWt.ensure(static_cast<size_t>(N) * K * 2);
+      pack_weight_bf16(dw, static_cast<__nv_bfloat16*>(dWt.p), K, N, K, 0);
+      dO.ensure(static_cast<size_t>(M) * N * 2);
+      __nv_bfloat16* dout = static_cast<__nv_bfloat16*>(dO.p);
+      GemmBf16 g = gemm_bf16_plan(da, K, static_cast<const __nv_bfloat16*>(dWt.p), K, dout, N, M, N, K, db, ds, dr, N, gelu != 0);
+      timed(iters, elapsed_ms, [&] { gemm_bf16_run(g, 0); });
+      download<__nv_bfloat16>(dout, out, static_cast<size_t>(M) * N);
+    }
+  });
+}
+
+int vb_op_attention(int32_t precision, int32_t variant, const float* q, const float* k, const float* v, const float* mix_a,
+                    const float* mix_b, const float* ln_gamma, const float* ln_beta, float* out, int32_t B, int32_t nq, int32_t nk,
+                    int32_t heads, int32_t dim_head, int32_t iters, float* elapsed_ms) {
+  return guarded(nullptr, [&] {
+    require_gpu();
+    VB_CHECK(q && k && v && out && B > 0 && nq > 0 && nk > 0 && heads > 0 && dim_head > 0, "vb_op_attention: bad arguments");
+    VB_CHECK(variant >= 0 && variant <= 2, "vb_op_attention: variant must be 0, 1 or 2");
+    const int inner = heads * dim_head;
+    DevMem dQ, dK, dV, dO, dS, dMa, dMb, dG, dBt;
+    const float* ma = mix_a ? upload<float>(dMa, mix_a, heads * heads) : nullptr;
+    const float* mb = mix_b ? upload<float>(dMb, mix_b, heads * heads) : nullptr;
+    const float* g = ln_gamma ? upload<float>(dG, ln_gamma, heads) : nullptr;
+    const float* bt = ln_beta ? upload<float>(dBt, ln_beta, heads) : nullptr;
+    const size_t cq = static_cast<size_t>(B) * nq * inner, ck = static_cast<size_t>(B) * nk * inner;
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      const T* q_d = upload<T>(dQ, q, cq);
+      const T* k_d = upload<T>(dK, k, ck);
+      const T* v_d = upload<T>(dV, v, ck);
+      dO.ensure(cq * sizeof(T));
+      T* o_d = static_cast<T*>(dO.p);
+      dS.ensure(static_cast<size_t>(B) * heads * nq * nk * 4);
+      timed(iters, elapsed_ms, [&] {
+        if (!attention_fast<T>(q_d, inner, k_d, inner, v_d, inner, o_d, inner, B, nq, nk, heads, dim_head, variant, ma, mb, g, bt, 0))
+          attention_generic<T>(q_d, inner, k_d, inner, v_d, inner, o_d, inner, static_cast<float*>(dS.p), B, nq, nk, heads,
+                               dim_head, variant, ma, mb, g, bt, 0);
+      });
+      download<T>(o_d, out, cq);
+    };
+    if (precision == VB_PRECISION_FP32) run(float());
+    else run(__nv_bfloat16());
+  });
+}
+
+int vb_op_layernorm(int32_t precision, const float* x, const float* gamma, const float* beta, float* out, int32_t M, int32_t D,
+                    int32_t iters, float* elapsed_ms) {
+  return guarded(nullptr, [&] {
+    require_gpu();
+    VB_CHECK(x && gamma && beta && out && M > 0 && D > 0, "vb_op_layernorm: bad arguments");
+    DevMem dX, dG, dB, dO;
+    const float* g = upload<float>(dG, gamma, D);
+    const float* b = upload<float>(dB, beta, D);
+    const size_t cnt = static_cast<size_t>(M) * D;
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      const T* x_d = upload<T>(dX, x, cnt);
+      dO.ensure(cnt * sizeof(T));
+      T* o_d = static_cast<T*>(dO.p);
+      timed(iters, elapsed_ms, [&] { layernorm<T>(x_d, D, g, b, o_d, D, M, D, 0); });
+      download<T>(o_d, out, cnt);
+    };
+    if (precision == VB_PRECISION_FP32) run(float());
+    else run(__nv_bfloat16());
+  });
+}
+
+}  // extern "C"

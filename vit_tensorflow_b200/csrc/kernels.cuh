@@ -1,0 +1,63 @@
+// Launch interfaces of the non-tensor-core kernels (kernels.cu).  T is float (exact-fp32 gate path) or
+// __nv_bfloat16 (activations of the tcgen05 path); all reductions / statistics are fp32.
+#pragma once
+#include "common.h"
+
+namespace vb {
+
+// im2col for non-overlapping patches: 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)' (vit.py:142).
+// img NHWC fp32 [B,H,W,C] -> out [B*(cls_row + gh*gw), ldo], columns [0, ph*pw*C) filled, [.., ldo) zeroed;
+// when cls_row == 1 the first row of every image is all zeros (its value comes from the GEMM epilogue).
+template <typename T>
+void im2col(const float* img, T* out, int B, int H, int W, int C, int ph, int pw, int cls_row, int ldo, cudaStream_t s);
+
+// R[b*rows + t, :] = pos[t, :] (+ cls - bias on t == 0 when has_cls): the additive term of the patch-embedding
+// GEMM epilogue that realises cls-token concat + pos_embedding add (vit.py:163-165, cait.py:184).
+template <typename T>
+void build_embed_residual(T* R, const float* pos, const float* cls, const float* bias, int B, int rows, int dim,
+                          int has_cls, cudaStream_t s);
+
+// LayerNorm over the last axis (Keras: eps 1e-3, biased variance; vit.py:18).  x [M, ldx] -> out [M, ldo].
+template <typename T>
+void layernorm(const T* x, int ldx, const float* gamma, const float* beta, T* out, int ldo, int M, int D, cudaStream_t s);
+
+// out[M,N] (TO) = epi(A[M,K] (TA, lda) x W), W element (k,n) at W[k*wsk + n*wsn]; fp32 FMA accumulation.
+// epi = (+bias) -> GELU(erf) -> (*scale) -> (+res[m*ldr + n]).
+template <typename TA, typename TW, typename TO>
+void gemm_simt(const TA* A, int lda, const TW* W, int wsk, int wsn, TO* out, int ldc, int M, int N, int K,
+               const float* bias, const float* scale, const TO* res, int ldr, int gelu, cudaStream_t s);
+
+// Generic attention through materialised scores (any n, d, variant), S fp32 [B,h,nq,nk] workspace.
+// q: [B, nq, *] rows of pitch ldq with head hh at columns [hh*dh, (hh+1)*dh); k, v likewise (nk rows per batch).
+template <typename T>
+void attn_scores(const T* q, int ldq, const T* k, int ldk, float* S, int B, int heads, int nq, int nk, int dh, float scale,
+                 cudaStream_t s);
+// In-place head mix: S[b,g,i,j] = sum_h S[b,h,i,j] * Wmix[h,g]; optional LayerNorm over g (gamma/beta [heads]).
+void attn_head_mix(float* S, const float* Wmix, const float* gamma, const float* beta, int B, int heads, int nq, int nk,
+                   cudaStream_t s);
+void attn_softmax(float* S, long long rows, int nk, cudaStream_t s);
+template <typename T>
+void attn_pv(const float* S, const T* v, int ldv, T* out, int ldo, int B, int heads, int nq, int nk, int dh, cudaStream_t s);
+
+// z[b,:] = LN(pool(X[b]))  with pool = row 0 (cls) or mean over the n rows; fp32 out [B, D].
+template <typename T>
+void pool_layernorm(const T* X, int n, int ldx, const float* gamma, const float* beta, float* out, int B, int D, int mean_pool,
+                    cudaStream_t s);
+
+// dst[b, doff + t, :] = src[b, soff + t, :], t < count  (token concat / slicing; batch pitches in rows).
+template <typename T>
+void copy_tokens(const T* src, int src_rows, int soff, T* dst, int dst_rows, int doff, int count, int B, int D, cudaStream_t s);
+// dst[b, 0, :] = vec (fp32) for every b (cls token broadcast, cait.py:189).
+template <typename T>
+void broadcast_row(const float* vec, T* dst, int dst_rows, int B, int D, cudaStream_t s);
+
+template <typename TI, typename TO>
+void convert(const TI* in, TO* out, long long count, cudaStream_t s);
+void add_inplace_f32(float* a, const float* b, long long count, cudaStream_t s);
+// Wt[n*ldw + k] = bf16(W[k*N + n]) : Keras [K,N] fp32 -> K-major bf16 rows (zero padded to ldw)
+void pack_weight_bf16(const float* W, __nv_bfloat16* Wt, int K, int N, int ldw, cudaStream_t s);
+
+long long launch_counter();      // number of kernel launches issued through these wrappers (process-wide)
+void count_launch(int n = 1);
+
+}  // namespace vb
