@@ -94,6 +94,14 @@ VB_API int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_m
 /* Kernels launched by this handle's most recent forward call. */
 VB_API int64_t vb_last_launch_count(vb_handle* h);
 
+/* Per-kernel-class device timing (CUDA events recorded on the launch stream around every launch of the class)
+ * for the roofline report.  Classes: 0 tcgen05 GEMM, 1 attention, 2 LayerNorm, 3 im2col, 4 other (SIMT fallbacks).
+ * vb_profile_read synchronises the device and returns accumulated milliseconds, algorithmic FLOPs, algorithmic
+ * bytes and launch counts per class (arrays of VB_PROF_NUM); reset != 0 clears the accumulators. */
+#define VB_PROF_NUM 5
+VB_API int vb_profile_enable(vb_handle* h, int32_t on);
+VB_API int vb_profile_read(vb_handle* h, double* ms, double* flops, double* bytes, int64_t* calls, int32_t reset);
+
 VB_API const char* vb_last_error(vb_handle* h);
 VB_API void vb_destroy(vb_handle* h);
 

@@ -126,6 +126,44 @@ struct vb_handle {
   DevMem img_dev, logits_dev, tok_dev;
   long long last_launches = 0;
 
+  // optional per-kernel-class timing: CUDA events recorded on the launch stream around each call
+  enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_EMBED = 3, PROF_OTHER = 4, PROF_NUM = 5 };
+  struct ProfRec { int cls; cudaEvent_t a, b; double flops; double bytes; };
+  bool profiling = false;
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[PROF_NUM] = {0}, prof_flops[PROF_NUM] = {0}, prof_bytes[PROF_NUM] = {0};
+  long long prof_calls[PROF_NUM] = {0};
+  cudaEvent_t get_event() {
+    if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    VB_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  struct ProfScope {
+    vb_handle* h; cudaStream_t s; int idx = -1;
+    ProfScope(vb_handle* h_, int cls, double flops, double bytes, cudaStream_t s_) : h(h_), s(s_) {
+      if (!h->profiling) return;
+      ProfRec r{cls, h->get_event(), h->get_event(), flops, bytes};
+      cudaEventRecord(r.a, s);
+      h->prof_recs.push_back(r);
+      idx = static_cast<int>(h->prof_recs.size()) - 1;
+    }
+    ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof_recs[idx].b, s); }
+  };
+  void prof_collect() {
+    if (prof_recs.empty()) return;
+    cudaDeviceSynchronize();
+    for (auto& r : prof_recs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+        prof_ms[r.cls] += ms; prof_flops[r.cls] += r.flops; prof_bytes[r.cls] += r.bytes; prof_calls[r.cls] += 1;
+      }
+      event_pool.push_back(r.a); event_pool.push_back(r.b);
+    }
+    prof_recs.clear();
+  }
+
   // model structure (filled by finalize)
   EmbedW embed, sm_embed, lg_embed;
   std::vector<LayerW> layers, cls_layers;
@@ -277,11 +315,11 @@ struct vb_handle {
     l.fc2 = make_linear(pre + "fc2", mlp, dim);
     return l;
   }
-  EmbedW make_embed(const std::string& pre, int p_h, int p_w, int dim, int n_pos) {
+  EmbedW make_embed(const std::string& pre, int p_h, int p_w, int dim, int n_pos, bool with_cls = true) {
     EmbedW e;
     e.patch = make_linear(pre + "patch", p_h * p_w * cfg.channels, dim);
     e.pos = W(pre + "pos_embedding");
-    e.cls = has(pre + "cls_token") ? W(pre + "cls_token") : nullptr;
+    e.cls = with_cls ? W(pre + "cls_token") : nullptr;   // CaiT adds its cls token after the patch stage (cait.py:189)
     e.dim = dim; e.n_pos = n_pos;
     return e;
   }
@@ -299,7 +337,7 @@ struct vb_handle {
       head = make_linear_f32("head", c.dim, c.num_classes);
     } else if (c.kind == VB_KIND_CAIT) {
       const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
-      embed = make_embed("", c.patch_h, c.patch_w, c.dim, np);
+      embed = make_embed("", c.patch_h, c.patch_w, c.dim, np, false);
       for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("patch_transformer.layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT));
       for (int L = 0; L < c.cls_depth; ++L) cls_layers.push_back(make_layer("cls_transformer.layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT));
       head_norm = make_norm("head_norm", c.dim);
@@ -384,7 +422,10 @@ struct vb_handle {
     const int Kp = bf16() ? e.patch.ldw : e.patch.K;
     const int M = B * rows;
     T* col = arena.get<T>(static_cast<size_t>(M) * Kp);
-    im2col<T>(img, col, B, H, Wd, cfg.channels, ph, pw, has_cls, Kp, s);
+    {
+      ProfScope ps(this, PROF_EMBED, 0.0, 4.0 * B * H * Wd * cfg.channels + static_cast<double>(sizeof(T)) * M * Kp, s);
+      im2col<T>(img, col, B, H, Wd, cfg.channels, ph, pw, has_cls, Kp, s);
+    }
     const T* R = embed_residual<T>(e, B, rows, s);
     T* X = arena.get<T>(static_cast<size_t>(M) * e.dim);
     Epi ep; ep.bias = e.patch.bias; ep.res = R; ep.ldr = e.dim;
@@ -401,7 +442,7 @@ struct vb_handle {
     const int M = B * rows, inner = l.heads * l.dim_head;
     T* Y = arena.get<T>(static_cast<size_t>(M) * dim);
     T* O = arena.get<T>(static_cast<size_t>(M) * inner);
-    layernorm<T>(X, dim, l.attn_norm.gamma, l.attn_norm.beta, Y, dim, M, dim, s);
+    ln<T>(X, l.attn_norm, Y, M, dim, s);
     if (l.fused_qkv) {
       T* QKV = arena.get<T>(static_cast<size_t>(M) * 3 * inner);
       linear<T>(Y, dim, M, l.to_qkv, QKV, 3 * inner, Epi(), s);
@@ -422,9 +463,14 @@ struct vb_handle {
     feed_forward<T>(X, M, dim, l, Y, s);
   }
   template <typename T>
+  void ln(const T* x, const Norm& n, T* y, int M, int dim, cudaStream_t s) {
+    ProfScope ps(this, PROF_LN, 0.0, 2.0 * sizeof(T) * M * dim, s);
+    layernorm<T>(x, dim, n.gamma, n.beta, y, dim, M, dim, s);
+  }
+  template <typename T>
   void feed_forward(T* X, int M, int dim, const LayerW& l, T* Y, cudaStream_t s) {
     T* Hb = arena.get<T>(static_cast<size_t>(M) * l.fc1.N);
-    layernorm<T>(X, dim, l.ff_norm.gamma, l.ff_norm.beta, Y, dim, M, dim, s);
+    ln<T>(X, l.ff_norm, Y, M, dim, s);
     Epi e1; e1.bias = l.fc1.bias; e1.gelu = true;
     linear<T>(Y, dim, M, l.fc1, Hb, l.fc1.N, e1, s);
     Epi e2; e2.bias = l.fc2.bias; e2.scale = l.ff_scale; e2.res = X; e2.ldr = dim;
@@ -570,7 +616,10 @@ void vb_handle::linear<__nv_bfloat16>(const __nv_bfloat16* A, int lda, int M, co
                                       const Epi& e, cudaStream_t s) {
   const int K = L.K;
   const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(e.res);
-  if (gemm_bf16_supported(M, L.N, K, lda, L.ldw, ldc) && (res == nullptr || e.ldr % 8 == 0)) {
+  const bool fast = gemm_bf16_supported(M, L.N, K, lda, L.ldw, ldc) && (res == nullptr || e.ldr % 8 == 0);
+  ProfScope ps(this, fast ? PROF_GEMM : PROF_OTHER, 2.0 * M * L.N * K,
+               2.0 * (static_cast<double>(M) * K + static_cast<double>(L.N) * K + static_cast<double>(M) * L.N * (res ? 2 : 1)), s);
+  if (fast) {
     PlanKey key{A, lda, L.Wt, out, ldc, M, L.N, K, e.bias, e.scale, res, e.ldr, e.gelu};
     auto it = plans.find(key);
     if (it == plans.end())
@@ -586,6 +635,8 @@ template <typename T>
 void vb_handle::attention_dispatch(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq,
                                    int nk, int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* g,
                                    const float* b, cudaStream_t s) {
+  ProfScope ps(this, PROF_ATTN, 4.0 * B * heads * nq * nk * dh + (variant == 1 ? 2.0 : variant == 2 ? 4.0 : 0.0) * B * nq * nk * heads * heads,
+               static_cast<double>(sizeof(T)) * B * heads * dh * (2.0 * nq + 2.0 * nk), s);
   if (attention_fast<T>(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s)) return;
   float* S = arena.get<float>(static_cast<size_t>(B) * heads * nq * nk);
   attention_generic<T>(q, ldq, k, ldk, v, ldv, out, ldo, S, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s);
@@ -823,12 +874,38 @@ int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_mem, int
 
 int64_t vb_last_launch_count(vb_handle* h) { return h ? h->last_launches : -1; }
 
+int vb_profile_enable(vb_handle* h, int32_t on) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr, "null handle");
+    VB_CUDA(cudaSetDevice(h->device));
+    h->prof_collect();
+    h->profiling = on != 0;
+  });
+}
+
+int vb_profile_read(vb_handle* h, double* ms, double* flops, double* bytes, int64_t* calls, int32_t reset) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr, "null handle");
+    VB_CUDA(cudaSetDevice(h->device));
+    h->prof_collect();
+    for (int i = 0; i < vb_handle::PROF_NUM; ++i) {
+      if (ms) ms[i] = h->prof_ms[i];
+      if (flops) flops[i] = h->prof_flops[i];
+      if (bytes) bytes[i] = h->prof_bytes[i];
+      if (calls) calls[i] = h->prof_calls[i];
+      if (reset) { h->prof_ms[i] = h->prof_flops[i] = h->prof_bytes[i] = 0; h->prof_calls[i] = 0; }
+    }
+  });
+}
+
 const char* vb_last_error(vb_handle* h) { return h ? h->error.c_str() : g_last_error.c_str(); }
 
 void vb_destroy(vb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   for (auto& w : h->weights) if (w.dev) cudaFree(w.dev);
+  h->prof_collect();
+  for (auto e : h->event_pool) cudaEventDestroy(e);
   delete h;
 }
 

@@ -190,6 +190,18 @@ class _EngineModel:
                                                out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
         return out
 
+    PROFILE_CLASSES = ("gemm_tcgen05", "attention", "layernorm", "im2col", "other")
+
+    def profile(self, on=True):
+        """Record CUDA events around every kernel class on the launch stream (for the roofline report)."""
+        _lib.check(self._lib.vb_profile_enable(self._h, int(bool(on))), self._h)
+
+    def profile_read(self, reset=True):
+        n = len(self.PROFILE_CLASSES)
+        ms, fl, by, calls = (C.c_double * n)(), (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(self._lib.vb_profile_read(self._h, ms, fl, by, calls, int(bool(reset))), self._h)
+        return {c: dict(ms=ms[i], flops=fl[i], bytes=by[i], launches=int(calls[i])) for i, c in enumerate(self.PROFILE_CLASSES)}
+
     @property
     def last_launch_count(self):
         return int(self._lib.vb_last_launch_count(self._h))

@@ -1,0 +1,121 @@
+"""Serving-side plumbing around the engine: data-parallel batch sharding and a host-buffer pipeline.
+
+torch is used here for what it is good at -- pinned host memory, CUDA streams/events and `torch.distributed`
+(NCCL over NVLink) -- and for nothing else: all model compute stays in libvitb200 behind the C-ABI.
+
+Data parallel: images are independent, so the global batch is split contiguously, rank r
+owning images [r*B, (r+1)*B); every rank holds a full weight replica; the forward has no communication; the only
+collective is ONE in-place all-gather of the fp32 logits (`[B, classes]` per rank), and the classifier-head kernel
+writes its logits directly into this rank's slice of the gather buffer, so compute -> collective needs no copy.
+"""
+from __future__ import annotations
+
+import os
+
+from . import _lib
+
+
+def shard_bounds(global_batch: int, world: int, rank: int):
+    """Contiguous shard [lo, hi) of rank `rank`; global_batch must divide evenly (static shapes, vit.py:161-163)."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def init_distributed(backend: str = "nccl"):
+    """One process per GPU, rendezvous from the torchrun environment.  Returns (rank, world, local_rank)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group(backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def all_gather_logits(gathered, local, world: int):
+    """In-place all-gather: `local` is this rank's slice of `gathered` ([world*B, classes])."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(gathered, local)
+    return gathered
+
+
+class DataParallel:
+    """Batch-sharded replica group around one engine model (one instance per process / GPU)."""
+
+    def __init__(self, model, per_rank_batch: int, image_hw, rank: int = 0, world: int = 1):
+        import torch
+        self.model, self.B, (self.h, self.w) = model, per_rank_batch, image_hw
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", model.device)
+        self.gathered = torch.empty((world * per_rank_batch, model.num_classes), dtype=torch.float32, device=self.dev)
+        self.local = self.gathered[rank * per_rank_batch:(rank + 1) * per_rank_batch]
+
+    def forward_device(self, img_dev):
+        """img_dev: this rank's shard, float32 NHWC CUDA tensor.  Returns the gathered logits (device tensor).
+        Asynchronous on torch's current stream."""
+        import torch
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        self.model.forward_raw(img_dev.data_ptr(), _lib.MEM_DEVICE, self.B, self.h, self.w, self.local.data_ptr(),
+                               _lib.MEM_DEVICE, stream)
+        return all_gather_logits(self.gathered, self.local, self.world)
+
+
+class HostPipeline:
+    """Host batches in -> host logits out, the call a serving user makes.
+
+    Step i copies its pinned-host image shard to the device on a copy stream while step i-1 computes
+    (double-buffered device inputs), runs the forward (+ all-gather) on the compute stream and copies the
+    gathered logits back to pinned host memory; `submit` returns the previous step's host logits."""
+
+    def __init__(self, dp: DataParallel):
+        import torch
+        self.dp = dp
+        dev = dp.dev
+        self.copy_stream = torch.cuda.Stream(dev)
+        self.compute_stream = torch.cuda.Stream(dev)
+        self.in_dev = [torch.empty((dp.B, dp.h, dp.w, 3), dtype=torch.float32, device=dev) for _ in range(2)]
+        self.out_host = [torch.empty(dp.gathered.shape, dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self.h2d_done = [torch.cuda.Event() for _ in range(2)]
+        self.step_done = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self.h2d_bytes = self.in_dev[0].numel() * 4
+        self.d2h_bytes = self.out_host[0].numel() * 4
+
+    def submit(self, img_host):
+        """img_host: pinned float32 NHWC CPU tensor [B,h,w,3].  Returns host logits of the previous submit (or None)."""
+        import torch
+        k = self.i & 1
+        with torch.cuda.stream(self.copy_stream):
+            if self.i >= 2:
+                self.copy_stream.wait_event(self.step_done[k])      # compute(i-2) no longer reads in_dev[k]
+            self.in_dev[k].copy_(img_host, non_blocking=True)
+            self.h2d_done[k].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.h2d_done[k])
+            g = self.dp.forward_device(self.in_dev[k])
+            self.out_host[k].copy_(g, non_blocking=True)
+            self.step_done[k].record(self.compute_stream)
+        prev = None
+        if self.i >= 1:
+            self.step_done[k ^ 1].synchronize()
+            prev = self.out_host[k ^ 1]
+        self.i += 1
+        return prev
+
+    def flush(self):
+        """Wait for and return the last submitted step's host logits."""
+        if self.i == 0:
+            return None
+        k = (self.i - 1) & 1
+        self.step_done[k].synchronize()
+        return self.out_host[k]
