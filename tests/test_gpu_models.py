@@ -2,7 +2,7 @@
 on identical seeded weights/inputs.
 
 fp32 engine path: BASELINE.json's gate, rtol=1e-3 / atol=1e-4 against the numpy-float64 spec.
-bf16 engine path (tcgen05): stated tolerance |err| <= 3e-2 + 3e-2*|ref| on O(1) logits (bf16 operands and bf16
+bf16 engine path (tcgen05): stated tolerance |err| <= 6e-2 + 4e-2*|ref| on O(1) logits (bf16 operands and bf16
 activations with fp32 accumulation; measured errors are recorded in DESIGN.md)."""
 import json
 import os
@@ -16,7 +16,7 @@ from cases import MID, SMALL, cfg_of
 pytestmark = pytest.mark.gpu
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-BF16_RTOL, BF16_ATOL = 3e-2, 3e-2
+BF16_RTOL, BF16_ATOL = 4e-2, 6e-2
 
 
 def _model(cfg, precision):

@@ -43,6 +43,7 @@ struct GemmBf16 {
   CUtensorMap tmap_a, tmap_b, tmap_c;
   int M = 0, N = 0, K = 0;
   int block_n = 256;
+  int cta_group = 2;                    // 2: CTA pairs (cta_group::2) on 256-row tiles; 1: single-CTA 128-row tiles
   const float* bias = nullptr;          // [N] or null
   const float* scale = nullptr;         // [N] or null (LayerScale)
   const __nv_bfloat16* res = nullptr;   // [M, ldr] or null (may alias out)

@@ -7,11 +7,16 @@
 // to_out + residual (vit.py:62-69,101), MLP fc1+GELU / fc2 + residual (vit.py:38-44,102), CaiT to_q/to_kv
 // (cait.py:94-95) with LayerScale folded in (cait.py:48).
 //
-// Structure (one CTA per SM, 384 threads, static round-robin tile scheduler):
-//   warp 0      TMA producer: A tile 128x64 + B tile BNx64 per k-block into a STAGES-deep 128B-swizzled ring
-//   warp 1      MMA issuer: one thread issues tcgen05.mma (128 x BN x 16) into a double-buffered TMEM accumulator
-//   warps 4-11  epilogue: tcgen05.ld -> bias/GELU/LayerScale/residual in registers -> bf16 -> swizzled smem
-//               staging (2 x 16 KB) -> TMA store.  Runs concurrently with the next tile's main loop.
+// Structure (one CTA per SM, 384 threads, static round-robin tile scheduler).  CG = 2 pairs two SMs
+// (cta_group::2, a 2-CTA cluster) on one 256 x BN tile: each CTA stages its own 128 A rows and HALF of the B rows,
+// the leader CTA issues M = 256 MMAs that read B from both CTAs' shared memory.  Per SM this cuts the TMA-write +
+// UMMA-read shared-memory traffic from 192 to 128 B/clk -- the 1-CTA form measured 65 % tensor-pipe activity
+// (profiles/r01_ncu_gemm_qkv_1cta.txt), exactly the 128/192 shared-memory-bandwidth bound.
+//   warp 0      TMA producer: A tile 128x64 + B tile (BN/CG)x64 per k-block into a STAGES-deep 128B-swizzled ring
+//   warp 1      MMA issuer (leader CTA): one thread issues tcgen05.mma (128*CG x BN x 16) into a double-buffered
+//               TMEM accumulator (each CTA holds its 128 rows)
+//   warps 4-11  epilogue: tcgen05.ld -> bias/GELU/LayerScale/residual in registers -> bf16 -> per-warp swizzled smem
+//               slab (8 x 4 KB) -> per-warp TMA store.  Runs concurrently with the next tile's main loop.
 #include "common.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -26,30 +31,44 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int NUM_EPI_THREADS = 256;
-constexpr int STAGING_BYTES = BM * 128;   // one 128-row x 64-col bf16 chunk
-constexpr int NUM_STAGING = 2;
+constexpr int STAGING_BYTES = 4096;       // per-warp slab: 32 rows x 64 bf16 columns (128-byte swizzled rows)
+constexpr int NUM_STAGING = 8;
 
-template <int BN>
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CG) * BK * 2;               // each CTA of a pair stages half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - 256 - 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 256 or 512)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STAGING * STAGING_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 };
 
+// Exact-erf GELU (vit.py:34) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-exact for a
+// bf16 result): 12 FMA-pipe instructions + 2 MUFU (rcp, ex2) instead of erff()'s ~28, which made the fc1 epilogue
+// (128 GELUs per thread per tile) slower than the tile's MMA time.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx(z * z * -1.4426950408889634f);
+  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), erf_abs, h);                // 0.5x + 0.5|x|erf(|x|/sqrt2) = 0.5x(1 + erf(x/sqrt2))
 }
 
-template <int BN, bool GELU, bool RES>
+template <int BN, bool GELU, bool RES, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const __nv_bfloat16* res, int ldr) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stage0 = smem_base;
@@ -65,10 +84,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tiles_m = (M + BM - 1) / BM;
+  constexpr int TM = BM * CG;                                      // rows per tile (per CTA pair when CG == 2)
+  const int tiles_m = (M + TM - 1) / TM;
   const int tiles_n = (N + BN - 1) / BN;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = (K + BK - 1) / BK;
+  const int cta_rank = (CG == 2) ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = cta_rank == 0;
+  const int tile0 = blockIdx.x / CG;                               // persistent schedule over clusters
+  const int tile_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -80,13 +104,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), NUM_EPI_THREADS / 32);
+      mbar_init(tempty_bar(s), CG * NUM_EPI_THREADS / 32);         // the leader counts both CTAs' epilogue warps
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+  if (warp == 1) {
+    if (CG == 2) tmem_alloc_cg2<C::TMEM_COLS>(tmem_ptr_smem); else tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
+  }
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();                                 // peer barriers are initialised before any remote signal
   tcgen05_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
@@ -95,29 +122,37 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * BM;
-        const int n0 = (t % tiles_n) * BN;
+      for (int t = tile0; t < num_tiles; t += tile_step) {
+        const int m0 = (t / tiles_n) * TM + cta_rank * BM;          // this CTA's 128 A rows
+        const int n0 = (t % tiles_n) * BN + cta_rank * (BN / CG);   // this CTA's share of the B rows
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_stage0 + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+          if (CG == 2) {
+            // both CTAs' bytes are counted on the leader's barrier, which expects the pair's total
+            const uint32_t lbar = full_bar(stage) & kPeerBitMask;
+            if (leader) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
+            tma_load_2d_cg2(sa, &tmap_a, lbar, kb * BK, m0);
+            tma_load_2d_cg2(sb, &tmap_b, lbar, kb * BK, n0);
+          } else {
+            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+          }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < num_tiles; t += tile_step) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -131,121 +166,134 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the 16-byte address field
-            umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (CG == 2) umma_f16_ss_cg2(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar(stage));             // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if (CG == 2) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));                 // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps of both CTAs
+        if (CG == 2) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp >= EPI_WARP0) {
     // ===================================================================== epilogue (8 warps)
+    // Warp (q, hf) owns accumulator rows [32q, 32q+32) (its TMEM lane quarter) and the column half hf of the tile,
+    // 64 columns (one 128-byte swizzled row) at a time, with a private 4 KB staging slab and its own TMA stores:
+    // no cross-warp barrier anywhere in the epilogue.
     const int e = warp - EPI_WARP0;
-    const int q = e & 3;          // TMEM lane quarter this warp may touch (warp_id % 4)
-    const int ch = e >> 2;        // which 32-column half of each 64-column chunk
+    const int q = e & 3;
+    const int hf = e >> 2;
     const int row_local = q * 32 + lane;
-    const bool is_store_thread = (threadIdx.x == EPI_WARP0 * 32);
+    const uint32_t slab = smem_staging + e * 4096;                 // 32 rows x 128 bytes, 1024-aligned
+    const uint32_t srow = slab + lane * 128;
+    constexpr int CHUNKS = BN / 128;                               // 64-column chunks per warp per tile
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t chunk_counter = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / tiles_n) * BM;
+    for (int t = tile0; t < num_tiles; t += tile_step) {
+      const int m0 = (t / tiles_n) * TM + cta_rank * BM;
       const int n0 = (t % tiles_n) * BN;
       const int row = m0 + row_local;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int ncol = n0 + c * 64 + ch * 32;
-        const bool col_ok = (n0 + c * 64) < N;       // N % 64 == 0: a chunk is entirely in or out
-        uint4 rres[4];
-        if (RES) {
-          if (col_ok && row < M) {
-            const uint4* rp = reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * ldr + ncol);
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int ncol0 = n0 + (hf * CHUNKS + c) * 64;
+        const bool col_ok = ncol0 < N;                              // N % 64 == 0: a chunk is entirely in or out
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + (hf * CHUNKS + c) * 64;
+        uint32_t packed[32];                                        // 64 bf16 outputs of this thread's row
 #pragma unroll
-            for (int k = 0; k < 4; ++k) rres[k] = rp[k];
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) rres[k] = make_uint4(0, 0, 0, 0);
-          }
-        }
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 64 + ch * 32, v);
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (col_ok) {
-          if (bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(bias + ncol);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 b4 = __ldg(bp + k);
-              f[4 * k + 0] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
-            }
-          }
-          if (GELU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          }
-          if (scale != nullptr) {
-            const float4* sp = reinterpret_cast<const float4*>(scale + ncol);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float4 s4 = __ldg(sp + k);
-              f[4 * k + 0] *= s4.x; f[4 * k + 1] *= s4.y; f[4 * k + 2] *= s4.z; f[4 * k + 3] *= s4.w;
-            }
-          }
+        for (int half = 0; half < 2; ++half) {
+          const int ncol = ncol0 + half * 32;
+          uint4 rres[4];
           if (RES) {
+            if (col_ok && row < M) {
+              const uint4* rp = reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * ldr + ncol);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const uint32_t w4[4] = {rres[k].x, rres[k].y, rres[k].z, rres[k].w};
+              for (int k = 0; k < 4; ++k) rres[k] = rp[k];
+            } else {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                f[8 * k + 2 * i + 0] += bf16_lo(w4[i]);
-                f[8 * k + 2 * i + 1] += bf16_hi(w4[i]);
+              for (int k = 0; k < 4; ++k) rres[k] = make_uint4(0, 0, 0, 0);
+            }
+          }
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tcol + half * 32, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (col_ok) {
+            if (bias != nullptr) {
+              const float4* bp = reinterpret_cast<const float4*>(bias + ncol);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 b4 = __ldg(bp + k);
+                f[4 * k + 0] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
+              }
+            }
+            if (GELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            }
+            if (scale != nullptr) {
+              const float4* sp = reinterpret_cast<const float4*>(scale + ncol);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float4 s4 = __ldg(sp + k);
+                f[4 * k + 0] *= s4.x; f[4 * k + 1] *= s4.y; f[4 * k + 2] *= s4.z; f[4 * k + 3] *= s4.w;
+              }
+            }
+            if (RES) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t w4[4] = {rres[k].x, rres[k].y, rres[k].z, rres[k].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  f[8 * k + 2 * i + 0] += bf16_lo(w4[i]);
+                  f[8 * k + 2 * i + 1] += bf16_hi(w4[i]);
+                }
               }
             }
           }
-        }
-        // staging buffer must have been fully read by the TMA store issued two chunks ago
-        const uint32_t buf = chunk_counter & 1u;
-        if (is_store_thread) bulk_wait_group_read<NUM_STAGING - 1>();
-        named_bar_sync(1, NUM_EPI_THREADS);
-        const uint32_t srow = smem_staging + buf * STAGING_BYTES + row_local * 128;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t slot = static_cast<uint32_t>((ch * 4 + k) ^ (row_local & 7));
-          const uint32_t p0 = pack_bf16x2(f[8 * k + 0], f[8 * k + 1]);
-          const uint32_t p1 = pack_bf16x2(f[8 * k + 2], f[8 * k + 3]);
-          const uint32_t p2 = pack_bf16x2(f[8 * k + 4], f[8 * k + 5]);
-          const uint32_t p3 = pack_bf16x2(f[8 * k + 6], f[8 * k + 7]);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + slot * 16), "r"(p0), "r"(p1), "r"(p2), "r"(p3) : "memory");
+          for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        }
+        // the slab must have been fully read by this warp's previous TMA store
+        if (lane == 0) bulk_wait_group_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t slot = static_cast<uint32_t>(k ^ (lane & 7));   // 128B swizzle: 16-byte slot ^ (row % 8)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + slot * 16), "r"(packed[4 * k]),
+                       "r"(packed[4 * k + 1]), "r"(packed[4 * k + 2]), "r"(packed[4 * k + 3]) : "memory");
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, NUM_EPI_THREADS);
-        if (is_store_thread) {
-          if (col_ok) tma_store_2d(&tmap_c, smem_staging + buf * STAGING_BYTES, n0 + c * 64, m0);
+        __syncwarp();
+        if (lane == 0) {
+          if (col_ok) tma_store_2d(&tmap_c, slab, ncol0, m0 + q * 32);
           bulk_commit_group();
         }
-        ++chunk_counter;
       }
       // all TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld above)
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);   // the leader's MMA warp owns this barrier
+        else mbar_arrive(tempty_bar(acc));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (is_store_thread) bulk_wait_group<0>();   // all output bytes are globally visible before exit
+    if (lane == 0) bulk_wait_group<0>();   // all output bytes are globally visible before exit
   }
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();     // no CTA exits (or frees TMEM) while its peer can still signal / read it
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if (CG == 2) tmem_dealloc_cg2<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -265,18 +313,35 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, bool GELU, bool RES>
+template <int BN, bool GELU, bool RES, int CG>
 void launch(const GemmBf16& g, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<BN, GELU, RES>;
+  auto kern = gemm_bf16_kernel<BN, GELU, RES, CG>;
   static bool configured = false;
   if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES));
+    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM_BYTES));
     configured = true;
   }
-  kern<<<g.grid, NUM_THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(g.tmap_a, g.tmap_b, g.tmap_c, g.M, g.N, g.K, g.bias, g.scale,
-                                                          g.res, g.ldr);
-  VB_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr));
   count_launch();
+}
+
+template <int BN, int CG>
+void launch_epi(const GemmBf16& g, cudaStream_t stream) {
+  const bool res = g.res != nullptr;
+  if (g.gelu) { if (res) launch<BN, true, true, CG>(g, stream); else launch<BN, true, false, CG>(g, stream); }
+  else        { if (res) launch<BN, false, true, CG>(g, stream); else launch<BN, false, false, CG>(g, stream); }
 }
 
 }  // namespace
@@ -336,22 +401,22 @@ GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt
   g.bias = bias; g.scale = scale; g.res = res; g.ldr = ldr; g.gelu = gelu;
   // 256-wide tiles unless N only fills 128-wide ones well (e.g. CaiT dim 384) or the problem is tiny.
   g.block_n = (N % 256 == 0 || N >= 1024) ? 256 : 128;
+  g.cta_group = (M > BM) ? 2 : 1;      // pair two SMs on 256-row tiles unless the whole problem is one 128-row tile
   g.tmap_a = make_tmap_2d(A, K, M, static_cast<uint64_t>(lda) * 2, BK, BM);
-  g.tmap_b = make_tmap_2d(Wt, K, N, static_cast<uint64_t>(ldw) * 2, BK, g.block_n);
-  g.tmap_c = make_tmap_2d(out, N, M, static_cast<uint64_t>(ldc) * 2, 64, BM);
-  const int tiles = ((M + BM - 1) / BM) * ((N + g.block_n - 1) / g.block_n);
-  g.grid = tiles < sm_count() ? tiles : sm_count();
+  g.tmap_b = make_tmap_2d(Wt, K, N, static_cast<uint64_t>(ldw) * 2, BK, g.block_n / g.cta_group);
+  g.tmap_c = make_tmap_2d(out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 32);
+  const int tm = BM * g.cta_group;
+  const int tiles = ((M + tm - 1) / tm) * ((N + g.block_n - 1) / g.block_n);
+  const int clusters = sm_count() / g.cta_group;
+  g.grid = (tiles < clusters ? tiles : clusters) * g.cta_group;
   return g;
 }
 
 void gemm_bf16_run(const GemmBf16& g, cudaStream_t stream) {
-  const bool res = g.res != nullptr;
-  if (g.block_n == 256) {
-    if (g.gelu) { if (res) launch<256, true, true>(g, stream); else launch<256, true, false>(g, stream); }
-    else        { if (res) launch<256, false, true>(g, stream); else launch<256, false, false>(g, stream); }
+  if (g.cta_group == 2) {
+    if (g.block_n == 256) launch_epi<256, 2>(g, stream); else launch_epi<128, 2>(g, stream);
   } else {
-    if (g.gelu) { if (res) launch<128, true, true>(g, stream); else launch<128, true, false>(g, stream); }
-    else        { if (res) launch<128, false, true>(g, stream); else launch<128, false, false>(g, stream); }
+    if (g.block_n == 256) launch_epi<256, 1>(g, stream); else launch_epi<128, 1>(g, stream);
   }
 }
 

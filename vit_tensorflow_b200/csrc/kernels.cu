@@ -398,10 +398,15 @@ __global__ void pool_layernorm_kernel(const T* __restrict__ X, int n, int ldx, c
     v = warp_sum(v);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
     __syncthreads();
-    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
-    t = warp_sum(t);
+    if (threadIdx.x < 32) {
+      float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) red[0] = t;
+    }
     __syncthreads();
-    return __shfl_sync(0xffffffffu, t, 0);
+    const float total = red[0];
+    __syncthreads();
+    return total;
   };
   float s = 0.f;
   for (int d = threadIdx.x; d < D; d += blockDim.x) s += z[d];
