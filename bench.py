@@ -113,16 +113,17 @@ def time_cpu_reference(c, budget_s, steps, warmup, log=None):
     cfg = oracle_cfg(c)
     w = oracle.init_weights(cfg, 0)
     ref = ref_torch.TorchReference(w, cfg)
-    probe = oracle.make_image(cfg, 2, 0)
-    ref(probe)
-    t0 = time.perf_counter(); ref(probe); t_img = (time.perf_counter() - t0) / 2
-    b = int(max(1, min(32, c["batch"], budget_s / max(1e-6, (steps + warmup) * t_img))))
+    b = int(min(32, c["batch"]))
     img = oracle.make_image(cfg, b, 1)
+    t_start = time.perf_counter()
     for _ in range(warmup):
         ref(img)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter(); ref(img); ts.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(ts) >= 1:
+            break
+    steps = len(ts)
     t = sum(ts) / len(ts)
     return dict(value=b / t, unit="images/s", cores=cores, kind="port",
                 sample=f"{steps} timed forwards of a {b}-image batch after {warmup} warm-up (torch {torch.__version__} CPU fp32 "

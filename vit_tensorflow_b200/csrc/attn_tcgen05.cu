@@ -13,10 +13,13 @@
 //   warp 1       MMA issuer: S_t = Q_t K^T (128 x 128 x 64, K-major operands) into TMEM, PV_t = P_t V
 //                (128 x 64 x 128; P K-major from shared memory, V MN-major exactly as TMA delivered it).  While
 //                warpgroup t runs its softmax on S_t, the tensor core works on tile 1-t.
-//   warps 4-7 / 8-11   softmax warpgroup 0 / 1: thread i owns query row i of its tile (TMEM lane i):
-//                tcgen05.ld of S, running max / sum in the exp2 domain, P written as bf16 into 128B-swizzled
-//                shared memory, running output row in registers (O = O * alpha + PV), final 1/l normalisation
-//                and a 128-byte row store in 'b n (h d)' order (the merge-heads rearrange, vit.py:82).
+//   warps 4-11 / 12-19  softmax group of tile 0 / 1: 8 warps per tile; query row i (TMEM lane i) is shared by two
+//                threads, one per 64-key half of every block (more warps per scheduler to hide the
+//                tcgen05.ld -> FFMA -> MUFU.EX2 dependency chains; ncu showed the 1-thread-per-row form
+//                latency-bound at IPC 0.5).  tcgen05.ld of S, running max / sum in the exp2 domain (row max
+//                exchanged through shared memory), P written as bf16 into 128B-swizzled shared memory, running
+//                output half-row in registers (O = O * alpha + PV), final 1/l normalisation and a 64-byte row
+//                store in 'b n (h d)' order (the merge-heads rearrange, vit.py:82).
 #include "attention.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -33,9 +36,10 @@ constexpr int BKV = 128;         // keys per block
 constexpr int KV_ST = 3;
 constexpr int TILE_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr int P_BYTES = 2 * TILE_BYTES;      // 128 rows x 128 keys bf16 as two 64-column swizzled blocks
-constexpr int ATT_THREADS = 384;
+constexpr int ATT_THREADS = 640;
 constexpr int SMEM_DATA = 2 * TILE_BYTES /*Q*/ + KV_ST * 2 * TILE_BYTES /*K,V*/ + 2 * P_BYTES;
-constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
+constexpr int XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [parity][tile][half][row] floats exchanged between the two threads of a row
+constexpr int ATT_SMEM = SMEM_DATA + XCHG_BYTES + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
 constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_PV + 64 t
 
@@ -49,7 +53,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t sK = sQ + 2 * TILE_BYTES;
   const uint32_t sV = sK + KV_ST * TILE_BYTES;
   const uint32_t sP = sV + KV_ST * TILE_BYTES;
-  const uint32_t bars = sP + 2 * P_BYTES;
+  const uint32_t sX = sP + 2 * P_BYTES;
+  const uint32_t bars = sX + XCHG_BYTES;
   auto q_full = [&](int t) { return bars + 8u * t; };
   auto q_empty = [&](int t) { return bars + 16u + 8u * t; };
   auto kv_full = [&](int s) { return bars + 32u + 8u * s; };
@@ -67,8 +72,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (threadIdx.x == 0) {
     for (int t = 0; t < 2; ++t) {
       mbar_init(q_full(t), 1); mbar_init(q_empty(t), 1);
-      mbar_init(s_full(t), 1); mbar_init(s_empty(t), 4);
-      mbar_init(p_full(t), 4); mbar_init(pv_full(t), 1);
+      mbar_init(s_full(t), 1); mbar_init(s_empty(t), 8);
+      mbar_init(p_full(t), 8); mbar_init(pv_full(t), 1);
     }
     for (int s = 0; s < KV_ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     fence_mbar_init();
@@ -161,44 +166,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ===================================================================== softmax warpgroups
-    const int t = (warp - 4) >> 2;
-    const int wq = warp & 3;
+    // ===================================================================== softmax groups (8 warps per tile)
+    const int wl = warp - 4;
+    const int t = wl >> 3;                  // tile slot
+    const int hf = (wl >> 2) & 1;           // which 64-key half of each block / which 32 output dims
+    const int wq = warp & 3;                // TMEM lane quarter
     const int row_local = wq * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t tS = lane_addr + TM_S + t * 128, tPV = lane_addr + TM_PV + t * 64;
-    const uint32_t sPt = sP + t * P_BYTES + row_local * 128;
-    uint32_t sc = 0, pvc = 0;
+    const uint32_t tS = lane_addr + TM_S + t * 128 + hf * 64, tPV = lane_addr + TM_PV + t * 64 + hf * 32;
+    const uint32_t sPt = sP + t * P_BYTES + hf * TILE_BYTES + row_local * 128;
+    const uint32_t pair_bar = 1 + t * 4 + wq;                              // named barrier of the two warps sharing rows
+    auto xchg = [&](uint32_t par, int half) { return sX + (((par * 2 + t) * 2 + half) * 128 + row_local) * 4; };
+    auto exchange = [&](uint32_t par, float mine) {                        // returns the partner thread's value
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xchg(par, hf)), "f"(mine) : "memory");
+      named_bar_sync(pair_bar, 64);
+      float other;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xchg(par, hf ^ 1)) : "memory");
+      return other;
+    };
+    uint32_t sc = 0, pvc = 0, xpar = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int pair = it % pairs, bh = it / pairs;
       const int h = bh % heads, b = bh / heads;
       const int q0 = pair * 2 * BQ + t * BQ;
       if (q0 >= nq) continue;                                             // this item has a single tile
-      float o[DH];
+      f32x2 o[16];                                                        // running output, 32 dims as fp32 pairs
 #pragma unroll
-      for (int d = 0; d < DH; ++d) o[d] = 0.f;
+      for (int d = 0; d < 16; ++d) o[d] = 0ull;
       float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int valid = min(BKV, nk - j * BKV);
-        const int nchunk = (valid + 31) >> 5;
+        const int nval = max(0, min(64, valid - hf * 64));                // valid keys among this thread's 64 columns
+        const int nfull = nval >> 5;                                      // full 32-key chunks
+        const int ntail = nval & 31;
         mbar_wait(s_full(t), sc & 1u);
         ++sc;
         tcgen05_fence_after();
-        // pass 1: row maximum of the raw scores
+        // pass 1: maximum of the raw scores over this thread's columns, then over the row
         float mx = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
+        for (int c = 0; c < nfull; ++c) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tS + c * 32, v);
           tmem_ld_wait();
-          if ((c + 1) * 32 <= valid) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
         }
+        if (ntail) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + nfull * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = (i < ntail) ? fmaxf(mx, __uint_as_float(v[i])) : mx;
+        }
+        mx = fmaxf(mx, exchange(xpar, mx));
+        xpar ^= 1u;
         const float m_new = fmaxf(m_run, mx * scale_log2);
         const float alpha = ex2_approx(m_run - m_new);                    // ex2(-inf) = 0 on the first block
         // fold the previous block's PV into the running output before its TMEM / P buffers are reused
@@ -206,43 +227,59 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(pv_full(t), pvc & 1u);
           ++pvc;
           tcgen05_fence_after();
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tPV, v);
+          tmem_ld_wait();
+          const f32x2 a2 = splat2(alpha_prev);
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(tPV + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha_prev, __uint_as_float(v[i]));
-          }
+          for (int i = 0; i < 16; ++i) o[i] = fma2(o[i], a2, pack2u(v[2 * i], v[2 * i + 1]));
         }
         // pass 2: probabilities -> bf16 -> swizzled shared memory (A operand of the PV product)
-        float rsum = 0.f;
-        for (int c = 0; c < nchunk; ++c) {
+        f32x2 rsum2 = 0ull;
+        const f32x2 sc2 = splat2(scale_log2), nm2 = splat2(-m_new);
+        auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t slot = static_cast<uint32_t>((c * 4 + k) ^ (row_local & 7));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + slot * 16), "r"(pk[4 * k]), "r"(pk[4 * k + 1]),
+                         "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3]) : "memory");
+          }
+        };
+        for (int c = 0; c < nfull; ++c) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(tS + c * 32, v);
           tmem_ld_wait();
           uint32_t pk[16];
-          const bool full = (c + 1) * 32 <= valid;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), scale_log2, -m_new));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), scale_log2, -m_new));
-            if (!full) {
-              if (c * 32 + 2 * i >= valid) p0 = 0.f;
-              if (c * 32 + 2 * i + 1 >= valid) p1 = 0.f;
-            }
-            rsum += p0 + p1;
+            float x0, x1;
+            unpack2(fma2(pack2u(v[2 * i], v[2 * i + 1]), sc2, nm2), x0, x1);
+            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            rsum2 = add2(rsum2, pack2(p0, p1));
             pk[i] = pack_bf16x2(p0, p1);
           }
-          const uint32_t rowp = sPt + (c >> 1) * TILE_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t slot = static_cast<uint32_t>(((c & 1) * 4 + k) ^ (row_local & 7));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + slot * 16), "r"(pk[4 * k]),
-                         "r"(pk[4 * k + 1]), "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3]) : "memory");
-          }
+          store_chunk(c, pk);
         }
-        l_run = fmaf(l_run, alpha, rsum);
+        if (ntail) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tS + nfull * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float x0, x1;
+            unpack2(fma2(pack2u(v[2 * i], v[2 * i + 1]), sc2, nm2), x0, x1);
+            float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+            p0 = (2 * i < ntail) ? p0 : 0.f;
+            p1 = (2 * i + 1 < ntail) ? p1 : 0.f;
+            rsum2 = add2(rsum2, pack2(p0, p1));
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          store_chunk(nfull, pk);
+        }
+        float rs0, rs1;
+        unpack2(rsum2, rs0, rs1);
+        l_run = fmaf(l_run, alpha, rs0 + rs1);
         m_run = m_new;
         alpha_prev = alpha;
         tcgen05_fence_before();
@@ -253,27 +290,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(pv_full(t), pvc & 1u);
       ++pvc;
       tcgen05_fence_after();
-      const float inv_l = 1.0f / l_run;
+      const float l_tot = l_run + exchange(xpar, l_run);                  // both halves of the row
+      xpar ^= 1u;
+      const float inv_l = 1.0f / l_tot;
       const int row = q0 + row_local;
-      __nv_bfloat16* orow = out + (static_cast<size_t>(b) * nq + row) * ldo + h * DH;
+      __nv_bfloat16* orow = out + (static_cast<size_t>(b) * nq + row) * ldo + h * DH + hf * 32;
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tPV, v);
+      tmem_ld_wait();
+      if (row < nq) {
+        const f32x2 a2 = splat2(alpha_prev), il2 = splat2(inv_l);
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tPV + c * 32, v);
-        tmem_ld_wait();
-        if (row < nq) {
+        for (int k = 0; k < 4; ++k) {
+          uint32_t pk[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int d = c * 32 + k * 8 + 2 * i;
-              const float a0 = fmaf(o[d], alpha_prev, __uint_as_float(v[k * 8 + 2 * i])) * inv_l;
-              const float a1 = fmaf(o[d + 1], alpha_prev, __uint_as_float(v[k * 8 + 2 * i + 1])) * inv_l;
-              pk[i] = pack_bf16x2(a0, a1);
-            }
-            *reinterpret_cast<uint4*>(orow + c * 32 + k * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int i = 0; i < 4; ++i) {
+            const int d = k * 4 + i;                                          // pair index: dims 2d, 2d+1
+            pk[i] = pack_bf16x2_from(mul2(fma2(o[d], a2, pack2u(v[2 * d], v[2 * d + 1])), il2));
           }
+          *reinterpret_cast<uint4*>(orow + k * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
       tcgen05_fence_before();

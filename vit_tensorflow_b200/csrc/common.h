@@ -50,6 +50,13 @@ struct GemmBf16 {
   int ldr = 0;
   bool gelu = false;
   int grid = 0;
+  // Folded LayerNorm of the A operand (Wt must hold gamma-scaled weights, bias the beta.W + b term):
+  //   out = rstd[m] * (acc - mu[m] * ln_c1[n]) + bias[n], with (mu, rstd) per row in ln_rows.
+  const float* ln_c1 = nullptr;
+  const float* ln_rows = nullptr;       // [M, 2] = (mu, rstd)
+  // Emit (sum, sumsq) of every 64-column chunk of the stored bf16 output rows: [M, N/64, 2]
+  float* stats_out = nullptr;
+  int stats_parts = 0;
 };
 // lda/ldw/ldc/ldr in elements; all must be multiples of 8 (16-byte TMA strides); N % 64 == 0.
 GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt, int ldw, __nv_bfloat16* out, int ldc,

@@ -10,7 +10,9 @@
 #include "common.h"
 #include "kernels.cuh"
 
+#include <array>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -81,6 +83,9 @@ struct Linear {
   const float* bias = nullptr;   // [N] or null
   __nv_bfloat16* Wt = nullptr;   // [N, ldw] bf16, K-major, zero padded
   int K = 0, N = 0, ldw = 0;
+  // LayerNorm folded into this Dense (bf16 engine): Wt holds gamma-scaled weights, ln_c2 replaces the bias
+  const float* ln_c1 = nullptr;
+  const float* ln_c2 = nullptr;
 };
 struct Norm { const float* gamma = nullptr; const float* beta = nullptr; int D = 0; };
 
@@ -90,6 +95,8 @@ struct Epi {
   const void* res = nullptr;
   int ldr = 0;
   bool gelu = false;
+  const float* ln_rows = nullptr;    // per-row (mean, rstd) of the A operand for a LayerNorm-folded Dense, [M, 2]
+  float* stats_out = nullptr;        // emit (sum, sumsq) partials of every 64-column chunk of the output rows, [M, N/64, 2]
 };
 
 struct LayerW {                    // one pre-norm transformer layer in any of the four dialects
@@ -102,6 +109,7 @@ struct LayerW {                    // one pre-norm transformer layer in any of t
   const float* attn_scale = nullptr;  // CaiT LayerScale
   const float* ff_scale = nullptr;
   int heads = 0, dim_head = 0, variant = 0;
+  bool folded = false;               // attn_norm / ff_norm folded into to_qkv (to_q, to_kv) / fc1
 };
 
 struct EmbedW { Linear patch; const float* pos = nullptr; const float* cls = nullptr; int dim = 0, n_pos = 0; };
@@ -177,7 +185,7 @@ struct vb_handle {
   std::map<ResKey, std::unique_ptr<DevMem>> embed_res;
 
   // cached tcgen05 GEMM plans (TMA descriptors)
-  using PlanKey = std::tuple<const void*, int, const void*, const void*, int, int, int, int, const void*, const void*, const void*, int, bool>;
+  using PlanKey = std::array<uintptr_t, 16>;
   std::map<PlanKey, GemmBf16> plans;
 
   bool bf16() const { return cfg.precision == VB_PRECISION_BF16; }
@@ -282,7 +290,7 @@ struct vb_handle {
   }
   bool has(const std::string& name) const { return windex.count(name) != 0; }
 
-  Linear make_linear(const std::string& n, int K, int N, bool bias = true) {
+  Linear make_linear(const std::string& n, int K, int N, bool bias = true, const Norm* fold = nullptr) {
     Linear L;
     L.W = W(n + ".kernel");
     L.bias = bias ? W(n + ".bias") : nullptr;
@@ -291,19 +299,31 @@ struct vb_handle {
       owned.emplace_back(new DevMem());
       owned.back()->ensure(static_cast<size_t>(N) * L.ldw * sizeof(__nv_bfloat16));
       L.Wt = static_cast<__nv_bfloat16*>(owned.back()->p);
-      pack_weight_bf16(L.W, L.Wt, K, N, L.ldw, 0);
+      pack_weight_bf16(L.W, L.Wt, K, N, L.ldw, 0, fold ? fold->gamma : nullptr);
+      if (fold) {
+        owned.emplace_back(new DevMem());
+        owned.back()->ensure(static_cast<size_t>(N) * 2 * sizeof(float));
+        float* c = static_cast<float*>(owned.back()->p);
+        ln_fold_consts(L.W, L.Wt, L.ldw, fold->beta, L.bias, c, c + N, K, N, 0);
+        L.ln_c1 = c; L.ln_c2 = c + N;
+      }
     }
     return L;
   }
   Norm make_norm(const std::string& n, int D) { return Norm{W(n + ".gamma"), W(n + ".beta"), D}; }
-  LayerW make_layer(const std::string& pre, int dim, int heads, int dh, int mlp, int kind) {
+  // fold_ok: the layer is only ever used as a self-attention layer (its LayerNorms feed nothing but GEMMs)
+  LayerW make_layer(const std::string& pre, int dim, int heads, int dh, int mlp, int kind, bool fold_ok = true) {
     LayerW l;
     const int inner = heads * dh;
     l.heads = heads; l.dim_head = dh;
     l.attn_norm = make_norm(pre + "attn_norm", dim);
     l.ff_norm = make_norm(pre + "ff_norm", dim);
-    if (kind == VB_KIND_VIT || kind == VB_KIND_DEEPVIT) { l.fused_qkv = true; l.to_qkv = make_linear(pre + "to_qkv", dim, 3 * inner, false); }
-    else { l.to_q = make_linear(pre + "to_q", dim, inner, false); l.to_kv = make_linear(pre + "to_kv", dim, 2 * inner, false); }
+    // LayerNorm folding needs every GEMM of the layer on the tcgen05 path (all widths multiples of 64)
+    l.folded = bf16() && fold_ok && dim % 64 == 0 && inner % 64 == 0 && mlp % 64 == 0 && getenv("VB_NO_LN_FOLD") == nullptr;
+    const Norm* fa = l.folded ? &l.attn_norm : nullptr;
+    const Norm* ff = l.folded ? &l.ff_norm : nullptr;
+    if (kind == VB_KIND_VIT || kind == VB_KIND_DEEPVIT) { l.fused_qkv = true; l.to_qkv = make_linear(pre + "to_qkv", dim, 3 * inner, false, fa); }
+    else { l.to_q = make_linear(pre + "to_q", dim, inner, false, fa); l.to_kv = make_linear(pre + "to_kv", dim, 2 * inner, false, fa); }
     if (kind == VB_KIND_DEEPVIT) { l.variant = 1; l.mix_a = W(pre + "reattn_weights"); l.reattn_norm = make_norm(pre + "reattn_norm", heads); }
     if (kind == VB_KIND_CAIT) {
       l.variant = 2; l.mix_a = W(pre + "mix_pre"); l.mix_b = W(pre + "mix_post");
@@ -311,7 +331,7 @@ struct vb_handle {
     }
     l.project_out = has(pre + "to_out.kernel");
     if (l.project_out) l.to_out = make_linear(pre + "to_out", inner, dim);
-    l.fc1 = make_linear(pre + "fc1", dim, mlp);
+    l.fc1 = make_linear(pre + "fc1", dim, mlp, true, ff);
     l.fc2 = make_linear(pre + "fc2", mlp, dim);
     return l;
   }
@@ -339,7 +359,7 @@ struct vb_handle {
       const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
       embed = make_embed("", c.patch_h, c.patch_w, c.dim, np, false);
       for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("patch_transformer.layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT));
-      for (int L = 0; L < c.cls_depth; ++L) cls_layers.push_back(make_layer("cls_transformer.layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT));
+      for (int L = 0; L < c.cls_depth; ++L) cls_layers.push_back(make_layer("cls_transformer.layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_CAIT, false));
       head_norm = make_norm("head_norm", c.dim);
       head = make_linear_f32("head", c.dim, c.num_classes);
     } else {
@@ -413,7 +433,8 @@ struct vb_handle {
 
   // patch embedding + cls token + pos embedding -> X [B*rows, dim]   (vit.py:160-165 / cait.py:181-184)
   template <typename T>
-  T* embed_tokens(const EmbedW& e, const float* img, int B, int H, int Wd, int ph, int pw, int* rows_out, cudaStream_t s) {
+  T* embed_tokens(const EmbedW& e, const float* img, int B, int H, int Wd, int ph, int pw, int* rows_out, cudaStream_t s,
+                  float** stats_out = nullptr) {
     VB_CHECK(H % ph == 0 && Wd % pw == 0, "Image dimensions must be divisible by the patch size.");
     const int np = (H / ph) * (Wd / pw);
     const int has_cls = e.cls != nullptr ? 1 : 0;
@@ -429,6 +450,10 @@ struct vb_handle {
     const T* R = embed_residual<T>(e, B, rows, s);
     T* X = arena.get<T>(static_cast<size_t>(M) * e.dim);
     Epi ep; ep.bias = e.patch.bias; ep.res = R; ep.ldr = e.dim;
+    if (stats_out != nullptr && bf16() && e.dim % 64 == 0 && getenv("VB_NO_LN_FOLD") == nullptr) {
+      *stats_out = arena.get<float>(static_cast<size_t>(M) * (e.dim / 64) * 2);
+      ep.stats_out = *stats_out;
+    }
     Linear L = e.patch;
     L.K = Kp;  // im2col zero-pads the patch vector to the packed weight pitch
     linear<T>(col, Kp, M, L, X, e.dim, ep, s);
@@ -436,44 +461,67 @@ struct vb_handle {
     return X;
   }
 
-  // one pre-norm layer, self-attention over all rows (vit.py:101-102, cait.py:150-151, cross_vit.py:109-111)
+  // one pre-norm layer, self-attention over all rows (vit.py:101-102, cait.py:150-151, cross_vit.py:109-111).
+  // `stats` (bf16 engine, folded layers): per-row (sum, sumsq) partials of X, valid on entry iff *stats_valid; the
+  // residual GEMMs keep them up to date, so no LayerNorm kernel runs at all.
   template <typename T>
-  void layer_self(T* X, int B, int rows, int dim, const LayerW& l, cudaStream_t s) {
+  void layer_self(T* X, int B, int rows, int dim, const LayerW& l, cudaStream_t s, float* stats = nullptr,
+                  bool* stats_valid = nullptr) {
     const int M = B * rows, inner = l.heads * l.dim_head;
+    const bool fold = l.folded && stats != nullptr;
+    if (fold && !*stats_valid) { ensure_stats(X, dim, stats, M, s); *stats_valid = true; }
     T* Y = arena.get<T>(static_cast<size_t>(M) * dim);
     T* O = arena.get<T>(static_cast<size_t>(M) * inner);
-    ln<T>(X, l.attn_norm, Y, M, dim, s);
+    float* lnrows = fold ? arena.get<float>(static_cast<size_t>(M) * 2) : nullptr;
+    const T* A = X;
+    Epi eq;
+    if (fold) { finalize_stats(stats, lnrows, M, dim, s); eq.ln_rows = lnrows; }
+    else { VB_CHECK(!l.folded, "internal: folded layer without statistics"); ln<T>(X, l.attn_norm, Y, M, dim, s); A = Y; }
     if (l.fused_qkv) {
       T* QKV = arena.get<T>(static_cast<size_t>(M) * 3 * inner);
-      linear<T>(Y, dim, M, l.to_qkv, QKV, 3 * inner, Epi(), s);
+      Epi e = eq; e.bias = l.to_qkv.ln_c2;
+      linear<T>(A, dim, M, l.to_qkv, QKV, 3 * inner, e, s);
       attention<T>(QKV, 3 * inner, QKV + inner, 3 * inner, QKV + 2 * inner, 3 * inner, O, inner, B, rows, rows, l, s);
     } else {
       T* Q = arena.get<T>(static_cast<size_t>(M) * inner);
       T* KV = arena.get<T>(static_cast<size_t>(M) * 2 * inner);
-      linear<T>(Y, dim, M, l.to_q, Q, inner, Epi(), s);
-      linear<T>(Y, dim, M, l.to_kv, KV, 2 * inner, Epi(), s);
+      Epi e1 = eq; e1.bias = l.to_q.ln_c2;
+      Epi e2 = eq; e2.bias = l.to_kv.ln_c2;
+      linear<T>(A, dim, M, l.to_q, Q, inner, e1, s);
+      linear<T>(A, dim, M, l.to_kv, KV, 2 * inner, e2, s);
       attention<T>(Q, inner, KV, 2 * inner, KV + inner, 2 * inner, O, inner, B, rows, rows, l, s);
     }
     if (l.project_out) {
       Epi e; e.bias = l.to_out.bias; e.scale = l.attn_scale; e.res = X; e.ldr = dim;
+      if (fold) e.stats_out = stats;
       linear<T>(O, inner, M, l.to_out, X, dim, e, s);
     } else {
       add_tokens<T>(X, O, static_cast<long long>(M) * dim, s);   // vit.py:53: identity out-projection
+      if (fold) ensure_stats(X, dim, stats, M, s);
     }
-    feed_forward<T>(X, M, dim, l, Y, s);
+    feed_forward<T>(X, M, dim, l, Y, s, fold ? stats : nullptr, lnrows);
   }
+  void finalize_stats(const float* stats, float* rows, int M, int dim, cudaStream_t s) {
+    ProfScope ps(this, PROF_LN, 0.0, 8.0 * M * (dim / 64) + 8.0 * M, s);
+    row_stats_finalize(stats, rows, M, dim / 64, dim, s);
+  }
+  template <typename T>
+  void ensure_stats(const T* X, int dim, float* stats, int M, cudaStream_t s);
   template <typename T>
   void ln(const T* x, const Norm& n, T* y, int M, int dim, cudaStream_t s) {
     ProfScope ps(this, PROF_LN, 0.0, 2.0 * sizeof(T) * M * dim, s);
     layernorm<T>(x, dim, n.gamma, n.beta, y, dim, M, dim, s);
   }
   template <typename T>
-  void feed_forward(T* X, int M, int dim, const LayerW& l, T* Y, cudaStream_t s) {
+  void feed_forward(T* X, int M, int dim, const LayerW& l, T* Y, cudaStream_t s, float* stats = nullptr, float* rows = nullptr) {
     T* Hb = arena.get<T>(static_cast<size_t>(M) * l.fc1.N);
-    ln<T>(X, l.ff_norm, Y, M, dim, s);
-    Epi e1; e1.bias = l.fc1.bias; e1.gelu = true;
-    linear<T>(Y, dim, M, l.fc1, Hb, l.fc1.N, e1, s);
+    Epi e1; e1.gelu = true;
+    const T* A = X;
+    if (stats != nullptr) { finalize_stats(stats, rows, M, dim, s); e1.ln_rows = rows; e1.bias = l.fc1.ln_c2; }
+    else { VB_CHECK(!l.folded, "internal: folded layer without statistics"); ln<T>(X, l.ff_norm, Y, M, dim, s); A = Y; e1.bias = l.fc1.bias; }
+    linear<T>(A, dim, M, l.fc1, Hb, l.fc1.N, e1, s);
     Epi e2; e2.bias = l.fc2.bias; e2.scale = l.ff_scale; e2.res = X; e2.ldr = dim;
+    e2.stats_out = stats;
     linear<T>(Hb, l.fc1.N, M, l.fc2, X, dim, e2, s);
   }
   template <typename T>
@@ -544,13 +592,17 @@ struct vb_handle {
     arena.reset();
     if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT) {
       int rows = 0;
-      T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s);
-      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s);
+      float* stats = nullptr;
+      T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s, &stats);
+      bool sv = stats != nullptr;
+      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s, stats, &sv);
       classify<T>(X, rows, c.dim, head_norm, head, B, c.pool == VB_POOL_MEAN, logits, false, s);
     } else if (c.kind == VB_KIND_CAIT) {
       int rows = 0;
-      T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s);
-      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s);
+      float* stats = nullptr;
+      T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s, &stats);
+      bool sv = stats != nullptr;
+      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s, stats, &sv);
       T* Cx = arena.get<T>(static_cast<size_t>(B) * c.dim);
       broadcast_row<T>(W("cls_token"), Cx, 1, B, c.dim, s);
       T* ctx = arena.get<T>(static_cast<size_t>(B) * (rows + 1) * c.dim);
@@ -559,17 +611,20 @@ struct vb_handle {
       classify<T>(Cx, 1, c.dim, head_norm, head, B, 0, logits, false, s);
     } else {
       int ns = 0, nl = 0;
-      T* S = embed_tokens<T>(sm_embed, img, B, H, Wd, c.sm_patch_size, c.sm_patch_size, &ns, s);
-      T* G = embed_tokens<T>(lg_embed, img, B, H, Wd, c.lg_patch_size, c.lg_patch_size, &nl, s);
+      float *st_s = nullptr, *st_g = nullptr;
+      T* S = embed_tokens<T>(sm_embed, img, B, H, Wd, c.sm_patch_size, c.sm_patch_size, &ns, s, &st_s);
+      T* G = embed_tokens<T>(lg_embed, img, B, H, Wd, c.lg_patch_size, c.lg_patch_size, &nl, s, &st_g);
+      bool sv_s = st_s != nullptr, sv_g = st_g != nullptr;
       T* sm_cls = arena.get<T>(static_cast<size_t>(B) * c.sm_dim);
       T* lg_cls = arena.get<T>(static_cast<size_t>(B) * c.lg_dim);
       T* ctx_lg = arena.get<T>(static_cast<size_t>(B) * nl * c.lg_dim);   // [LN(Pin(sm_cls)) ; lg patches]
       T* ctx_sm = arena.get<T>(static_cast<size_t>(B) * ns * c.sm_dim);   // [LN(Pin(lg_cls)) ; sm patches]
       for (const auto& xb : xblocks) {
-        for (const auto& l : xb.sm_layers) layer_self<T>(S, B, ns, c.sm_dim, l, s);
+        for (const auto& l : xb.sm_layers) layer_self<T>(S, B, ns, c.sm_dim, l, s, st_s, &sv_s);
         layernorm<T>(S, c.sm_dim, xb.sm_final.gamma, xb.sm_final.beta, S, c.sm_dim, B * ns, c.sm_dim, s);
-        for (const auto& l : xb.lg_layers) layer_self<T>(G, B, nl, c.lg_dim, l, s);
+        for (const auto& l : xb.lg_layers) layer_self<T>(G, B, nl, c.lg_dim, l, s, st_g, &sv_g);
         layernorm<T>(G, c.lg_dim, xb.lg_final.gamma, xb.lg_final.beta, G, c.lg_dim, B * nl, c.lg_dim, s);
+        sv_s = sv_g = false;   // the trailing LayerNorm and the cls write-back below change the token rows
         copy_tokens<T>(S, ns, 0, sm_cls, 1, 0, 1, B, c.sm_dim, s);
         copy_tokens<T>(G, nl, 0, lg_cls, 1, 0, 1, B, c.lg_dim, s);
         copy_tokens<T>(G, nl, 1, ctx_lg, nl, 1, nl - 1, B, c.lg_dim, s);
@@ -599,7 +654,9 @@ struct vb_handle {
       X = arena.get<T>(count);
       convert<float, __nv_bfloat16>(tok, reinterpret_cast<__nv_bfloat16*>(X), count, s);
     }
-    for (const auto& l : layers) layer_self<T>(X, B, n, cfg.dim, l, s);
+    float* stats = (bf16() && cfg.dim % 64 == 0 && getenv("VB_NO_LN_FOLD") == nullptr) ? arena.get<float>(static_cast<size_t>(B) * n * (cfg.dim / 64) * 2) : nullptr;
+    bool sv = false;
+    for (const auto& l : layers) layer_self<T>(X, B, n, cfg.dim, l, s, stats, &sv);
     if (sizeof(T) == 4) VB_CUDA(cudaMemcpyAsync(out, X, count * 4, cudaMemcpyDeviceToDevice, s));
     else convert<__nv_bfloat16, float>(reinterpret_cast<const __nv_bfloat16*>(X), out, count, s);
   }
@@ -617,18 +674,41 @@ void vb_handle::linear<__nv_bfloat16>(const __nv_bfloat16* A, int lda, int M, co
   const int K = L.K;
   const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(e.res);
   const bool fast = gemm_bf16_supported(M, L.N, K, lda, L.ldw, ldc) && (res == nullptr || e.ldr % 8 == 0);
+  const bool folded = L.ln_c1 != nullptr;
+  VB_CHECK(!folded || (fast && e.ln_rows != nullptr), "internal: LayerNorm-folded Dense needs the tcgen05 path and row statistics");
+  VB_CHECK(e.stats_out == nullptr || fast, "internal: row statistics requested from a non-tcgen05 GEMM");
   ProfScope ps(this, fast ? PROF_GEMM : PROF_OTHER, 2.0 * M * L.N * K,
                2.0 * (static_cast<double>(M) * K + static_cast<double>(L.N) * K + static_cast<double>(M) * L.N * (res ? 2 : 1)), s);
   if (fast) {
-    PlanKey key{A, lda, L.Wt, out, ldc, M, L.N, K, e.bias, e.scale, res, e.ldr, e.gelu};
+    PlanKey key{};
+    const uintptr_t parts[16] = {reinterpret_cast<uintptr_t>(A), static_cast<uintptr_t>(lda), reinterpret_cast<uintptr_t>(L.Wt),
+                                 reinterpret_cast<uintptr_t>(out), static_cast<uintptr_t>(ldc), static_cast<uintptr_t>(M),
+                                 static_cast<uintptr_t>(L.N), static_cast<uintptr_t>(K), reinterpret_cast<uintptr_t>(e.bias),
+                                 reinterpret_cast<uintptr_t>(e.scale), reinterpret_cast<uintptr_t>(res),
+                                 static_cast<uintptr_t>(e.ldr), static_cast<uintptr_t>(e.gelu),
+                                 reinterpret_cast<uintptr_t>(e.ln_rows), reinterpret_cast<uintptr_t>(L.ln_c1),
+                                 reinterpret_cast<uintptr_t>(e.stats_out)};
+    for (int i = 0; i < 16; ++i) key[i] = parts[i];
     auto it = plans.find(key);
-    if (it == plans.end())
-      it = plans.emplace(key, gemm_bf16_plan(A, lda, L.Wt, L.ldw, out, ldc, M, L.N, K, e.bias, e.scale, res, e.ldr, e.gelu)).first;
+    if (it == plans.end()) {
+      GemmBf16 g = gemm_bf16_plan(A, lda, L.Wt, L.ldw, out, ldc, M, L.N, K, e.bias, e.scale, res, e.ldr, e.gelu);
+      if (folded) { g.ln_c1 = L.ln_c1; g.ln_rows = e.ln_rows; }
+      if (e.stats_out) { g.stats_out = e.stats_out; g.stats_parts = L.N / 64; }
+      it = plans.emplace(key, g).first;
+    }
     gemm_bf16_run(it->second, s);
   } else {
     gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(A, lda, L.Wt, 1, L.ldw, out, ldc, M, L.N, K, e.bias, e.scale, res,
                                                            e.ldr, e.gelu ? 1 : 0, s);
   }
+}
+
+template <>
+void vb_handle::ensure_stats<float>(const float*, int, float*, int, cudaStream_t) {}
+template <>
+void vb_handle::ensure_stats<__nv_bfloat16>(const __nv_bfloat16* X, int dim, float* stats, int M, cudaStream_t s) {
+  ProfScope ps(this, PROF_LN, 0.0, 2.0 * M * dim, s);
+  row_stats_bf16(X, dim, stats, M, dim, s);
 }
 
 template <typename T>

@@ -46,20 +46,27 @@ struct Cfg {
 };
 
 // Exact-erf GELU (vit.py:34) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-exact for a
-// bf16 result): 12 FMA-pipe instructions + 2 MUFU (rcp, ex2) instead of erff()'s ~28, which made the fc1 epilogue
-// (128 GELUs per thread per tile) slower than the tile's MMA time.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx(z * z * -1.4426950408889634f);
-  const float erf_abs = fmaf(-p, e, 1.0f);          // erf(|x|/sqrt2)
-  const float h = 0.5f * x;
-  return fmaf(fabsf(h), erf_abs, h);                // 0.5x + 0.5|x|erf(|x|/sqrt2) = 0.5x(1 + erf(x/sqrt2))
+// bf16 result), evaluated on fp32 PAIRS: 13 FFMA2/FMUL2 + 4 MUFU (rcp, ex2) per two elements instead of erff()'s
+// ~28 instructions per element, which made the fc1 epilogue (128 GELUs per thread per tile) slower than the MMAs.
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  const f32x2 ax = abs2(x);
+  const f32x2 z = mul2(ax, splat2(0.70710678118654752440f));
+  const f32x2 den = fma2(splat2(0.3275911f), z, splat2(1.0f));
+  float d0, d1;
+  unpack2(den, d0, d1);
+  const f32x2 t = pack2(rcp_approx(d0), rcp_approx(d1));
+  f32x2 p = fma2(splat2(-1.061405429f), t, splat2(1.453152027f));      // coefficients negated: p = -poly(t)
+  p = fma2(p, t, splat2(-1.421413741f));
+  p = fma2(p, t, splat2(0.284496736f));
+  p = fma2(p, t, splat2(-0.254829592f));
+  p = mul2(p, t);
+  const f32x2 zz = mul2(mul2(z, z), splat2(-1.4426950408889634f));
+  float e0, e1;
+  unpack2(zz, e0, e1);
+  const f32x2 e = pack2(ex2_approx(e0), ex2_approx(e1));
+  const f32x2 erf_abs = fma2(p, e, splat2(1.0f));                      // erf(|x|/sqrt2)
+  const f32x2 h = mul2(x, splat2(0.5f));
+  return fma2(abs2(h), erf_abs, h);                                    // 0.5x + 0.5|x|erf(|x|/sqrt2)
 }
 
 template <int BN, bool GELU, bool RES, int CG>
@@ -67,7 +74,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
-                 const __nv_bfloat16* res, int ldr) {
+                 const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* __restrict__ ln_rows,
+                 float2* __restrict__ stats_out, int stats_parts) {
   using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -192,10 +200,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     constexpr int CHUNKS = BN / 128;                               // 64-column chunks per warp per tile
     int acc = 0;
     uint32_t acc_phase = 0;
+    // folded LayerNorm of the A operand: y = rstd * acc + (-rstd * mu) * c1[n] + c2[n]   (c2 arrives through `bias`);
+    // (mu, rstd) of this thread's row, prefetched one tile ahead
+    float2 ln_next = make_float2(0.f, 1.f);
+    if (ln_rows != nullptr && tile0 < num_tiles) {
+      const int r0 = (tile0 / tiles_n) * TM + cta_rank * BM + row_local;
+      if (r0 < M) ln_next = ln_rows[r0];
+    }
     for (int t = tile0; t < num_tiles; t += tile_step) {
       const int m0 = (t / tiles_n) * TM + cta_rank * BM;
       const int n0 = (t % tiles_n) * BN;
       const int row = m0 + row_local;
+      const f32x2 ln_rstd2 = splat2(ln_next.y);
+      const f32x2 ln_nmr2 = splat2(-ln_next.x * ln_next.y);
+      if (ln_rows != nullptr && t + tile_step < num_tiles) {
+        const int rn = ((t + tile_step) / tiles_n) * TM + cta_rank * BM + row_local;
+        if (rn < M) ln_next = ln_rows[rn];
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -221,28 +242,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint32_t v[32];
           tmem_ld_32x32b_x32(tcol + half * 32, v);
           tmem_ld_wait();
-          float f[32];
+          f32x2 f[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) f[j] = pack2u(v[2 * j], v[2 * j + 1]);
           if (col_ok) {
-            if (bias != nullptr) {
-              const float4* bp = reinterpret_cast<const float4*>(bias + ncol);
+            if (ln_c1 != nullptr) {
+              const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(ln_c1 + ncol);
+              const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const float4 b4 = __ldg(bp + k);
-                f[4 * k + 0] += b4.x; f[4 * k + 1] += b4.y; f[4 * k + 2] += b4.z; f[4 * k + 3] += b4.w;
+                const ulonglong2 c4 = __ldg(cp + k), b4 = __ldg(bp + k);
+                f[2 * k + 0] = fma2(f[2 * k + 0], ln_rstd2, fma2(c4.x, ln_nmr2, b4.x));
+                f[2 * k + 1] = fma2(f[2 * k + 1], ln_rstd2, fma2(c4.y, ln_nmr2, b4.y));
+              }
+            } else if (bias != nullptr) {
+              const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const ulonglong2 b4 = __ldg(bp + k);
+                f[2 * k + 0] = add2(f[2 * k + 0], b4.x);
+                f[2 * k + 1] = add2(f[2 * k + 1], b4.y);
               }
             }
             if (GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+              for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
             }
             if (scale != nullptr) {
-              const float4* sp = reinterpret_cast<const float4*>(scale + ncol);
+              const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(scale + ncol);
 #pragma unroll
               for (int k = 0; k < 8; ++k) {
-                const float4 s4 = __ldg(sp + k);
-                f[4 * k + 0] *= s4.x; f[4 * k + 1] *= s4.y; f[4 * k + 2] *= s4.z; f[4 * k + 3] *= s4.w;
+                const ulonglong2 s4 = __ldg(sp + k);
+                f[2 * k + 0] = mul2(f[2 * k + 0], s4.x);
+                f[2 * k + 1] = mul2(f[2 * k + 1], s4.y);
               }
             }
             if (RES) {
@@ -250,15 +282,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int k = 0; k < 4; ++k) {
                 const uint32_t w4[4] = {rres[k].x, rres[k].y, rres[k].z, rres[k].w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  f[8 * k + 2 * i + 0] += bf16_lo(w4[i]);
-                  f[8 * k + 2 * i + 1] += bf16_hi(w4[i]);
-                }
+                for (int i = 0; i < 4; ++i) f[4 * k + i] = add2(f[4 * k + i], bf16x2_to_f32x2(w4[i]));
               }
             }
           }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16x2_from(f[j]);
+        }
+        // (sum, sum of squares) of this row's 64 stored bf16 outputs: LayerNorm statistics for the consumer GEMM
+        if (stats_out != nullptr && col_ok && row < M) {
+          f32x2 s1 = 0ull, s2 = 0ull;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const f32x2 ab = bf16x2_to_f32x2(packed[j]);
+            s1 = add2(s1, ab);
+            s2 = fma2(ab, ab, s2);
+          }
+          float a0, a1, b0, b1;
+          unpack2(s1, a0, a1);
+          unpack2(s2, b0, b1);
+          stats_out[static_cast<size_t>(row) * stats_parts + (ncol0 >> 6)] = make_float2(a0 + a1, b0 + b1);
         }
         // the slab must have been fully read by this warp's previous TMA store
         if (lane == 0) bulk_wait_group_read<0>();
@@ -333,7 +376,8 @@ void launch(const GemmBf16& g, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr));
+  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
+                             reinterpret_cast<const float2*>(g.ln_rows), reinterpret_cast<float2*>(g.stats_out), g.stats_parts));
   count_launch();
 }
 

@@ -456,18 +456,70 @@ __global__ void add_inplace_kernel(float* __restrict__ a, const float* __restric
 }
 
 // 32x32 smem-transposed: reads W[k,n] coalesced along n, writes Wt[n,k] coalesced along k
-__global__ void pack_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int ldw) {
+__global__ void pack_weight_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt, int K, int N, int ldw,
+                                   const float* __restrict__ row_scale) {
   __shared__ float tile[32][33];
   const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int k = k0 + r, n = n0 + threadIdx.x;
-    tile[r][threadIdx.x] = (k < K && n < N) ? W[static_cast<long long>(k) * N + n] : 0.f;
+    float v = (k < K && n < N) ? W[static_cast<long long>(k) * N + n] : 0.f;
+    if (row_scale != nullptr && k < K) v *= row_scale[k];
+    tile[r][threadIdx.x] = v;
   }
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int n = n0 + r, k = k0 + threadIdx.x;
     if (n < N && k < ldw) Wt[static_cast<long long>(n) * ldw + k] = __float2bfloat16_rn(tile[threadIdx.x][r]);
   }
+}
+
+// one warp per output column n
+__global__ void ln_fold_consts_kernel(const float* __restrict__ W, const __nv_bfloat16* __restrict__ Wt, int ldw,
+                                      const float* __restrict__ beta, const float* __restrict__ bias, float* __restrict__ c1,
+                                      float* __restrict__ c2, int K, int N) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    a += __bfloat162float(Wt[static_cast<long long>(n) * ldw + k]);
+    b = fmaf(beta[k], W[static_cast<long long>(k) * N + n], b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { c1[n] = a; c2[n] = b + (bias ? bias[n] : 0.f); }
+}
+
+// one thread per (row, 64-column chunk)
+__global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, float2* __restrict__ stats, int M, int parts) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<long long>(M) * parts) return;
+  const int c = static_cast<int>(idx % parts);
+  const long long m = idx / parts;
+  const uint4* p = reinterpret_cast<const uint4*>(X + m * ldx + c * 64);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 v = p[i];
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = __uint_as_float(w4[j] << 16), b = __uint_as_float(w4[j] & 0xFFFF0000u);
+      s1 += a + b;
+      s2 = fmaf(a, a, fmaf(b, b, s2));
+    }
+  }
+  stats[idx] = make_float2(s1, s2);
+}
+
+__global__ void row_stats_finalize_kernel(const float2* __restrict__ stats, float2* __restrict__ rows, int M, int parts, float inv_d) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  const float2* p = stats + static_cast<long long>(m) * parts;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = 0; i < parts; ++i) { const float2 v = p[i]; s1 += v.x; s2 += v.y; }
+  const float mu = s1 * inv_d;
+  rows[m] = make_float2(mu, rsqrtf(fmaxf(s2 * inv_d - mu * mu, 0.f) + 1e-3f));
 }
 
 inline int grid_1d(long long total, int block = 256) {
@@ -596,9 +648,29 @@ void add_inplace_f32(float* a, const float* b, long long count, cudaStream_t s) 
   VB_LAUNCHED();
 }
 
-void pack_weight_bf16(const float* W, __nv_bfloat16* Wt, int K, int N, int ldw, cudaStream_t s) {
+void pack_weight_bf16(const float* W, __nv_bfloat16* Wt, int K, int N, int ldw, cudaStream_t s, const float* row_scale) {
   dim3 grid((N + 31) / 32, (ldw + 31) / 32);
-  pack_weight_kernel<<<grid, dim3(32, 8), 0, s>>>(W, Wt, K, N, ldw);
+  pack_weight_kernel<<<grid, dim3(32, 8), 0, s>>>(W, Wt, K, N, ldw, row_scale);
+  VB_LAUNCHED();
+}
+
+void ln_fold_consts(const float* W, const __nv_bfloat16* Wt, int ldw, const float* beta, const float* bias, float* c1, float* c2,
+                    int K, int N, cudaStream_t s) {
+  ln_fold_consts_kernel<<<(N + 7) / 8, 256, 0, s>>>(W, Wt, ldw, beta, bias, c1, c2, K, N);
+  VB_LAUNCHED();
+}
+
+void row_stats_finalize(const float* stats, float* rows, int M, int parts, int D, cudaStream_t s) {
+  row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float2*>(stats), reinterpret_cast<float2*>(rows), M,
+                                                          parts, 1.0f / static_cast<float>(D));
+  VB_LAUNCHED();
+}
+
+void row_stats_bf16(const __nv_bfloat16* X, int ldx, float* stats, int M, int D, cudaStream_t s) {
+  VB_CHECK(D % 64 == 0 && ldx % 8 == 0, "row_stats_bf16: D must be a multiple of 64");
+  const int parts = D / 64;
+  const long long total = static_cast<long long>(M) * parts;
+  row_stats_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(X, ldx, reinterpret_cast<float2*>(stats), M, parts);
   VB_LAUNCHED();
 }
 

@@ -55,7 +55,17 @@ template <typename TI, typename TO>
 void convert(const TI* in, TO* out, long long count, cudaStream_t s);
 void add_inplace_f32(float* a, const float* b, long long count, cudaStream_t s);
 // Wt[n*ldw + k] = bf16(W[k*N + n]) : Keras [K,N] fp32 -> K-major bf16 rows (zero padded to ldw)
-void pack_weight_bf16(const float* W, __nv_bfloat16* Wt, int K, int N, int ldw, cudaStream_t s);
+// row_scale (may be null): Wt[n*ldw + k] = bf16(W[k*N + n] * row_scale[k])  (LayerNorm gamma folded into the weight)
+void pack_weight_bf16(const float* W, __nv_bfloat16* Wt, int K, int N, int ldw, cudaStream_t s, const float* row_scale = nullptr);
+// Constants of a LayerNorm folded into the following Dense (see gemm_tcgen05.cu):
+//   c1[n] = sum_k float(Wt[n,k])   (the gamma-scaled, bf16-rounded weights the tensor core really multiplies)
+//   c2[n] = sum_k beta[k] * W[k,n] + (bias ? bias[n] : 0)
+void ln_fold_consts(const float* W, const __nv_bfloat16* Wt, int ldw, const float* beta, const float* bias, float* c1, float* c2,
+                    int K, int N, cudaStream_t s);
+// stats[m, c] = (sum, sum of squares) of X[m, 64c .. 64c+63]  (same format the GEMM epilogue emits); D % 64 == 0
+void row_stats_bf16(const __nv_bfloat16* X, int ldx, float* stats, int M, int D, cudaStream_t s);
+// rows[m] = (mean, rsqrt(var + 1e-3)) from the `parts` (sum, sumsq) partials of row m over D elements (fixed order)
+void row_stats_finalize(const float* stats, float* rows, int M, int parts, int D, cudaStream_t s);
 
 long long launch_counter();      // number of kernel launches issued through these wrappers (process-wide)
 void count_launch(int n = 1);

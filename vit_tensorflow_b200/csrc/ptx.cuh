@@ -245,6 +245,47 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// ------------------------------------------------------------------------------------------ packed fp32x2 math
+// Blackwell issues two fp32 FMAs per lane per instruction (SASS FFMA2 / FMUL2 / FADD2) on 64-bit register pairs.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 abs2(f32x2 a) { return a & 0x7FFFFFFF7FFFFFFFull; }
+__device__ __forceinline__ uint32_t pack_bf16x2_from(f32x2 v) {       // bf16(lo) in bits 0-15, bf16(hi) in bits 16-31
+  float lo, hi;
+  unpack2(v, lo, hi);
+  __nv_bfloat162 r = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ f32x2 bf16x2_to_f32x2(uint32_t w) { return pack2u(w << 16, w & 0xFFFF0000u); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
