@@ -95,10 +95,12 @@ VB_API int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_m
 VB_API int64_t vb_last_launch_count(vb_handle* h);
 
 /* Per-kernel-class device timing (CUDA events recorded on the launch stream around every launch of the class)
- * for the roofline report.  Classes: 0 tcgen05 GEMM, 1 attention, 2 LayerNorm, 3 im2col, 4 other (SIMT fallbacks).
+ * for the roofline report.  Classes: 0 tcgen05 GEMM (plain / LayerNorm-folded epilogue: to_qkv, to_q, to_kv), 1 attention,
+ * 2 LayerNorm / row statistics, 3 im2col, 4 other (SIMT fallbacks), 5 tcgen05 GEMM with GELU epilogue (fc1),
+ * 6 tcgen05 GEMM with residual epilogue (patch embed, to_out, fc2).
  * vb_profile_read synchronises the device and returns accumulated milliseconds, algorithmic FLOPs, algorithmic
  * bytes and launch counts per class (arrays of VB_PROF_NUM); reset != 0 clears the accumulators. */
-#define VB_PROF_NUM 5
+#define VB_PROF_NUM 7
 VB_API int vb_profile_enable(vb_handle* h, int32_t on);
 VB_API int vb_profile_read(vb_handle* h, double* ms, double* flops, double* bytes, int64_t* calls, int32_t reset);
 

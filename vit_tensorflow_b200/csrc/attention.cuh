@@ -18,4 +18,6 @@ bool attention_fast(const T* q, int ldq, const T* k, int ldk, const T* v, int ld
                     int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* ln_gamma,
                     const float* ln_beta, cudaStream_t s);
 
+long long*& attn_trace_buffer();   // debugging aid: device trace buffer of the tcgen05 attention kernel (null = off)
+
 }  // namespace vb

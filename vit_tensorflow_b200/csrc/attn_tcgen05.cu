@@ -10,16 +10,20 @@
 //                the fused to_qkv) through 3-D tensor maps (box 64 x 128 x 1): the head split
 //                'b n (h d) -> b h n d' (vit.py:74) costs nothing, and rows past n are zero-filled by TMA instead
 //                of bleeding into the next image.
-//   warp 1       MMA issuer: S_t = Q_t K^T (128 x 128 x 64, K-major operands) into TMEM, PV_t = P_t V
-//                (128 x 64 x 128; P K-major from shared memory, V MN-major exactly as TMA delivered it).  While
-//                warpgroup t runs its softmax on S_t, the tensor core works on tile 1-t.
-//   warps 4-11 / 12-19  softmax group of tile 0 / 1: 8 warps per tile; query row i (TMEM lane i) is shared by two
-//                threads, one per 64-key half of every block (more warps per scheduler to hide the
-//                tcgen05.ld -> FFMA -> MUFU.EX2 dependency chains; ncu showed the 1-thread-per-row form
-//                latency-bound at IPC 0.5).  tcgen05.ld of S, running max / sum in the exp2 domain (row max
-//                exchanged through shared memory), P written as bf16 into 128B-swizzled shared memory, running
-//                output half-row in registers (O = O * alpha + PV), final 1/l normalisation and a 64-byte row
-//                store in 'b n (h d)' order (the merge-heads rearrange, vit.py:82).
+//   warps 1, 2    MMA issuers, one per query tile (independent pipelines): S_t = Q_t K^T (128 x 128 x 64,
+//                K-major operands) into TMEM, O_t += P_t V (128 x 64 x 128; P K-major from shared memory, V MN-major
+//                exactly as TMA delivered it).  S(k+1) is issued BEFORE PV(k): the softmax group keeps S in
+//                registers, so the S buffer is free again long before P(k) is ready -- a clock64 trace of the
+//                single-issuer form (profiles/r01_attn_trace_v5.txt) showed the softmax groups waiting 1.6-2 K
+//                cycles per block for S and the issuer thread spending ~100 cycles per MMA on descriptor math.
+//   warps 4-7 / 8-11  softmax group of tile 0 / 1: thread i owns query row i of its tile (TMEM lane i).
+//                S is read from TMEM exactly ONCE per block (tcgen05.ld -> 128 registers: TMEM->register bandwidth,
+//                not MUFU, bounded the earlier two-pass forms -- see profiles/), the S buffer is released to the
+//                tensor core immediately, max / exp2 / sum run on registers with packed fp32x2 math, P goes as bf16
+//                into 128B-swizzled shared memory.  O accumulates in TMEM across key blocks (MMA accumulate); the
+//                softmax reference point only moves -- and O is only rescaled in TMEM -- when a block's row max
+//                exceeds it by more than 2^8 (exact; FlashAttention-4-style lazy rescale).  Final 1/l normalisation
+//                and a 128-byte row store in 'b n (h d)' order (the merge-heads rearrange, vit.py:82).
 #include "attention.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -36,25 +40,23 @@ constexpr int BKV = 128;         // keys per block
 constexpr int KV_ST = 3;
 constexpr int TILE_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr int P_BYTES = 2 * TILE_BYTES;      // 128 rows x 128 keys bf16 as two 64-column swizzled blocks
-constexpr int ATT_THREADS = 640;
+constexpr int ATT_THREADS = 384;             // warp 0 TMA, warps 1-2 MMA issuers, warp 3 idle, warps 4-7 / 8-11 softmax
 constexpr int SMEM_DATA = 2 * TILE_BYTES /*Q*/ + KV_ST * 2 * TILE_BYTES /*K,V*/ + 2 * P_BYTES;
-constexpr int XCHG_BYTES = 2 * 2 * 2 * 128 * 4;  // [parity][tile][half][row] floats exchanged between the two threads of a row
-constexpr int ATT_SMEM = SMEM_DATA + XCHG_BYTES + 256 + 1024;
+constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
 constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_PV + 64 t
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ out, int ldo, int heads, int nq, int nk,
-                int num_items, float scale_log2) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, int heads, int nq, int nk,
+                int num_items, float scale_log2, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
   const uint32_t sK = sQ + 2 * TILE_BYTES;
   const uint32_t sV = sK + KV_ST * TILE_BYTES;
   const uint32_t sP = sV + KV_ST * TILE_BYTES;
-  const uint32_t sX = sP + 2 * P_BYTES;
-  const uint32_t bars = sX + XCHG_BYTES;
+  const uint32_t bars = sP + 2 * P_BYTES;
   auto q_full = [&](int t) { return bars + 8u * t; };
   auto q_empty = [&](int t) { return bars + 16u + 8u * t; };
   auto kv_full = [&](int s) { return bars + 32u + 8u * s; };
@@ -72,10 +74,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (threadIdx.x == 0) {
     for (int t = 0; t < 2; ++t) {
       mbar_init(q_full(t), 1); mbar_init(q_empty(t), 1);
-      mbar_init(s_full(t), 1); mbar_init(s_empty(t), 8);
-      mbar_init(p_full(t), 8); mbar_init(pv_full(t), 1);
+      mbar_init(s_full(t), 1); mbar_init(s_empty(t), 4);
+      mbar_init(p_full(t), 4); mbar_init(pv_full(t), 1);
     }
-    for (int s = 0; s < KV_ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int s = 0; s < KV_ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }   // one release per tile issuer
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
@@ -84,11 +86,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // optional timeline trace (VB_ATTN_TRACE=1 through vb_op_attention): CTA 0 records (tag, clock) pairs per role
+  int dbg_n = 0;
+  auto trace = [&](int role, int tag) {
+    if (dbg != nullptr && blockIdx.x == 0 && dbg_n < 250) {
+      dbg[role * 512 + 2 * dbg_n] = tag;
+      dbg[role * 512 + 2 * dbg_n + 1] = clock64();
+      ++dbg_n;
+    }
+  };
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
-      tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+    // ===================================================================== TMA producer (warp-uniform loop, elected lane issues)
+    {
+      if (lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); }
       uint32_t kv_cnt = 0, qcnt[2] = {0, 0};
       for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
         const int pair = it % pairs, bh = it / pairs;
@@ -97,224 +108,292 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int ntiles = (nq - row0 > BQ) ? 2 : 1;
         for (int t = 0; t < ntiles; ++t) {
           mbar_wait(q_empty(t), (qcnt[t] & 1u) ^ 1u);
-          mbar_arrive_expect_tx(q_full(t), TILE_BYTES);
-          tma_load_3d(sQ + t * TILE_BYTES, &tmap_q, q_full(t), h * DH, row0 + t * BQ, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(q_full(t), TILE_BYTES);
+            tma_load_3d(sQ + t * TILE_BYTES, &tmap_q, q_full(t), h * DH, row0 + t * BQ, b);
+          }
+          __syncwarp();
           ++qcnt[t];
         }
         for (int j = 0; j < nblk; ++j) {
           const int st = kv_cnt % KV_ST;
           mbar_wait(kv_empty(st), ((kv_cnt / KV_ST) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(kv_full(st), 2 * TILE_BYTES);
-          tma_load_3d(sK + st * TILE_BYTES, &tmap_k, kv_full(st), h * DH, j * BKV, b);
-          tma_load_3d(sV + st * TILE_BYTES, &tmap_v, kv_full(st), h * DH, j * BKV, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(kv_full(st), 2 * TILE_BYTES);
+            tma_load_3d(sK + st * TILE_BYTES, &tmap_k, kv_full(st), h * DH, j * BKV, b);
+            tma_load_3d(sV + st * TILE_BYTES, &tmap_v, kv_full(st), h * DH, j * BKV, b);
+          }
+          __syncwarp();
           ++kv_cnt;
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t kv_cnt = 0;               // K/V blocks consumed before this item
-      uint32_t qn[2] = {0, 0};           // Q tiles consumed per tile slot
-      uint32_t sn[2] = {0, 0};           // S products issued per tile slot
-      uint32_t pn[2] = {0, 0};           // PV products issued per tile slot
-      for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-        const int pair = it % pairs;
-        const int row0 = pair * 2 * BQ;
-        const int ntiles = (nq - row0 > BQ) ? 2 : 1;
-        auto issue_s = [&](int t, int j) {
-          const uint32_t c = kv_cnt + j;
-          const int st = c % KV_ST;
-          mbar_wait(kv_full(st), (c / KV_ST) & 1u);
-          if (sn[t] > 0) mbar_wait(s_empty(t), (sn[t] - 1) & 1u);     // softmax has read the previous S_t
-          tcgen05_fence_after();
-          const int valid = min(BKV, nk - j * BKV);
-          const uint32_t idesc = make_idesc_bf16(BQ, (valid + 15) & ~15, 0, 0);
-          const uint64_t dq = make_smem_desc(sQ + t * TILE_BYTES, 16, 1024, 2);
-          const uint64_t dk = make_smem_desc(sK + st * TILE_BYTES, 16, 1024, 2);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tmem_base + TM_S + t * 128, dq + 2u * k, dk + 2u * k, idesc, k != 0);
-          umma_commit(s_full(t));
-          ++sn[t];
-          if (j == nblk - 1) umma_commit(q_empty(t));                  // last use of Q_t for this item
-        };
-        for (int t = 0; t < ntiles; ++t) { mbar_wait(q_full(t), qn[t] & 1u); ++qn[t]; }
-        for (int t = 0; t < ntiles; ++t) issue_s(t, 0);
-        for (int j = 0; j < nblk; ++j) {
-          const uint32_t c = kv_cnt + j;
-          const int st = c % KV_ST;
-          const int valid = min(BKV, nk - j * BKV);
-          const int ksteps = (valid + 15) >> 4;
-          constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);    // B (= V) is MN-major
-          for (int t = 0; t < ntiles; ++t) {
-            mbar_wait(p_full(t), pn[t] & 1u);                              // P_t(j) is in shared memory
-            tcgen05_fence_after();
-            for (int s = 0; s < ksteps; ++s) {
-              // A = P: 16 keys = 32 bytes inside a 64-key swizzled block; blocks are 16 KB apart
-              const uint64_t dp = make_smem_desc(sP + t * P_BYTES + (s >> 2) * TILE_BYTES + (s & 3) * 32, 16, 1024, 2);
-              // B = V: rows are keys (the MMA K dimension); 16 keys = 2 swizzle atoms of 8 rows x 128 bytes
-              const uint64_t dv = make_smem_desc(sV + st * TILE_BYTES + s * 2048, 8192, 1024, 2);
-              umma_f16_ss(tmem_base + TM_PV + t * 64, dp, dv, idesc_pv, s != 0);
-            }
-            umma_commit(pv_full(t));
-            ++pn[t];
-            if (j + 1 < nblk) issue_s(t, j + 1);
-          }
-          umma_commit(kv_empty(st));                                       // both tiles are done with K_j / V_j
+  } else if (warp == 1 || warp == 2) {
+    // ===================================================================== MMA issuer of tile t (warp-uniform loop)
+    {
+      const int t = warp - 1;
+      const uint32_t tS_d = tmem_base + TM_S + t * 128, tO_d = tmem_base + TM_PV + t * 64;
+      const uint64_t dq = make_smem_desc(sQ + t * TILE_BYTES, 16, 1024, 2);
+      const uint64_t dk0 = make_smem_desc(sK, 16, 1024, 2);
+      const uint64_t dp = make_smem_desc(sP + t * P_BYTES, 16, 1024, 2);
+      const uint64_t dv0 = make_smem_desc(sV, 8192, 1024, 2);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BQ, DH, 0, 1);       // B (= V) is MN-major
+      constexpr uint32_t ST16 = TILE_BYTES >> 4;                           // descriptor address units per stage / P block
+      uint32_t sn = 0, pn = 0, qn = 0;
+      // flat (item, block) cursor for S products; `kv` = global K/V block counter of the cursor's block
+      struct Cur { int it; int j; uint32_t kv; bool ok; };
+      auto has_tile = [&](int it) { return (nq - (it % pairs) * 2 * BQ) > t * BQ; };
+      auto first = [&]() {
+        Cur c{static_cast<int>(blockIdx.x), 0, 0u, false};
+        while (c.it < num_items && !has_tile(c.it)) { c.it += gridDim.x; c.kv += nblk; }
+        c.ok = c.it < num_items;
+        return c;
+      };
+      auto advance = [&](Cur c) {
+        ++c.kv;
+        if (++c.j == nblk) {
+          c.j = 0;
+          c.it += gridDim.x;
+          while (c.it < num_items && !has_tile(c.it)) { c.it += gridDim.x; c.kv += nblk; }
         }
-        kv_cnt += nblk;
+        c.ok = c.it < num_items;
+        return c;
+      };
+      // Issue S for cursor c.  blocking = false: only if Q / K are already resident (the run-ahead before PV(k) must
+      // never wait on loads that themselves wait for PV(k)'s stage release -- that deadlocked at n = 577).
+      auto issue_s = [&](const Cur& c, bool blocking) -> bool {
+        const uint32_t st = c.kv % KV_ST;
+        if (!blocking) {
+          bool ready = mbar_try_wait(kv_full(st), (c.kv / KV_ST) & 1u);
+          if (c.j == 0) ready = ready && mbar_try_wait(q_full(t), qn & 1u);
+          if (!__all_sync(0xffffffffu, ready)) return false;
+        }
+        if (c.j == 0) { mbar_wait(q_full(t), qn & 1u); ++qn; }
+        mbar_wait(kv_full(st), (c.kv / KV_ST) & 1u);
+        if (sn > 0) mbar_wait(s_empty(t), (sn - 1) & 1u);                  // softmax holds the previous S_t in registers
+        tcgen05_fence_after();
+        const int valid = min(BKV, nk - c.j * BKV);
+        const uint32_t idesc = make_idesc_bf16(BQ, (valid + 15) & ~15, 0, 0);
+        const uint64_t dk = dk0 + st * ST16;
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma_f16_ss(tS_d, dq + 2u * k, dk + 2u * k, idesc, k != 0);
+          umma_commit(s_full(t));
+          if (c.j == nblk - 1) umma_commit(q_empty(t));                    // last use of Q_t for this item
+          trace(t == 0 ? 0 : 3, 100 + c.j);
+        }
+        __syncwarp();
+        ++sn;
+        return true;
+      };
+      Cur cur = first();
+      if (cur.ok) issue_s(cur, true);
+      while (cur.ok) {
+        const Cur nxt = advance(cur);
+        const bool early = nxt.ok && issue_s(nxt, false);                  // S(k+1) before PV(k) when its inputs are resident
+        const uint32_t st = cur.kv % KV_ST;
+        const int valid = min(BKV, nk - cur.j * BKV);
+        const int ksteps = (valid + 15) >> 4;
+        mbar_wait(p_full(t), pn & 1u);                                     // P_t(k) is in shared memory
+        ++pn;
+        tcgen05_fence_after();
+        const uint64_t dv = dv0 + st * ST16;
+        const bool solo = (t == 0) && (nq - (cur.it % pairs) * 2 * BQ) <= BQ;   // item without a second tile
+        if (elect_one()) {
+#pragma unroll
+          for (int s8 = 0; s8 < BKV / 16; ++s8) {
+            // A = P: 16 keys = 32 bytes inside a 64-key swizzled block (blocks 16 KB apart);
+            // B = V: 16 keys = 2 swizzle atoms of 8 rows x 128 bytes
+            if (s8 < ksteps)
+              umma_f16_ss(tO_d, dp + ((s8 >> 2) * ST16 + (s8 & 3) * 2), dv + s8 * 128u, idesc_pv, (cur.j | s8) != 0);
+          }
+          umma_commit(pv_full(t));
+          umma_commit(kv_empty(st));
+          if (solo) umma_commit(kv_empty(st));
+          trace(t == 0 ? 0 : 3, 400 + cur.j);
+        }
+        __syncwarp();
+        if (nxt.ok && !early) issue_s(nxt, true);
+        cur = nxt;
       }
     }
-  } else if (warp >= 4) {
-    // ===================================================================== softmax groups (8 warps per tile)
-    const int wl = warp - 4;
-    const int t = wl >> 3;                  // tile slot
-    const int hf = (wl >> 2) & 1;           // which 64-key half of each block / which 32 output dims
-    const int wq = warp & 3;                // TMEM lane quarter
+  } else {
+    // ===================================================================== softmax groups (4 warps per tile)
+    if (warp == 3) goto done;               // spare warp
+    const int t = (warp - 4) >> 2;          // tile slot
+    const int wq = warp & 3;                // TMEM lane quarter this warp may access
     const int row_local = wq * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t tS = lane_addr + TM_S + t * 128 + hf * 64, tPV = lane_addr + TM_PV + t * 64 + hf * 32;
-    const uint32_t sPt = sP + t * P_BYTES + hf * TILE_BYTES + row_local * 128;
-    const uint32_t pair_bar = 1 + t * 4 + wq;                              // named barrier of the two warps sharing rows
-    auto xchg = [&](uint32_t par, int half) { return sX + (((par * 2 + t) * 2 + half) * 128 + row_local) * 4; };
-    auto exchange = [&](uint32_t par, float mine) {                        // returns the partner thread's value
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xchg(par, hf)), "f"(mine) : "memory");
-      named_bar_sync(pair_bar, 64);
-      float other;
-      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xchg(par, hf ^ 1)) : "memory");
-      return other;
-    };
-    uint32_t sc = 0, pvc = 0, xpar = 0;
+    const uint32_t tS = lane_addr + TM_S + t * 128, tPV = lane_addr + TM_PV + t * 64;
+    const uint32_t sPt = sP + t * P_BYTES + row_local * 128;
+    uint32_t sc = 0, pvc = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int pair = it % pairs, bh = it / pairs;
       const int h = bh % heads, b = bh / heads;
       const int q0 = pair * 2 * BQ + t * BQ;
       if (q0 >= nq) continue;                                             // this item has a single tile
-      f32x2 o[16];                                                        // running output, 32 dims as fp32 pairs
-#pragma unroll
-      for (int d = 0; d < 16; ++d) o[d] = 0ull;
-      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+      float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int valid = min(BKV, nk - j * BKV);
-        const int nval = max(0, min(64, valid - hf * 64));                // valid keys among this thread's 64 columns
-        const int nfull = nval >> 5;                                      // full 32-key chunks
-        const int ntail = nval & 31;
+        if (wq == 0 && lane == 0) trace(1 + t, 10 + j);
         mbar_wait(s_full(t), sc & 1u);
         ++sc;
         tcgen05_fence_after();
-        // pass 1: maximum of the raw scores over this thread's columns, then over the row
+        if (wq == 0 && lane == 0) trace(1 + t, 20 + j);
+        // the only TMEM read of S: this row's 128 scores
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld_32x32b_x32(tS, v0);
+        tmem_ld_32x32b_x32(tS + 32, v1);
+        tmem_ld_32x32b_x32(tS + 64, v2);
+        tmem_ld_32x32b_x32(tS + 96, v3);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(t));                           // the tensor core may overwrite S_t now
         float mx = -INFINITY;
-        for (int c = 0; c < nfull; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + c * 32, v);
-          tmem_ld_wait();
+        auto chunk_max = [&](int c, const uint32_t (&v)[32]) {             // full / partial / empty 32-key chunk
+          const int nv = valid - c * 32;
+          if (nv >= 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-        if (ntail) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + nfull * 32, v);
-          tmem_ld_wait();
+            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+          } else if (nv > 0) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = (i < ntail) ? fmaxf(mx, __uint_as_float(v[i])) : mx;
-        }
-        mx = fmaxf(mx, exchange(xpar, mx));
-        xpar ^= 1u;
-        const float m_new = fmaxf(m_run, mx * scale_log2);
-        const float alpha = ex2_approx(m_run - m_new);                    // ex2(-inf) = 0 on the first block
-        // fold the previous block's PV into the running output before its TMEM / P buffers are reused
-        if (j > 0) {
-          mbar_wait(pv_full(t), pvc & 1u);
-          ++pvc;
-          tcgen05_fence_after();
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tPV, v);
-          tmem_ld_wait();
-          const f32x2 a2 = splat2(alpha_prev);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = fma2(o[i], a2, pack2u(v[2 * i], v[2 * i + 1]));
-        }
-        // pass 2: probabilities -> bf16 -> swizzled shared memory (A operand of the PV product)
-        f32x2 rsum2 = 0ull;
-        const f32x2 sc2 = splat2(scale_log2), nm2 = splat2(-m_new);
-        auto store_chunk = [&](int c, const uint32_t (&pk)[16]) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t slot = static_cast<uint32_t>((c * 4 + k) ^ (row_local & 7));
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + slot * 16), "r"(pk[4 * k]), "r"(pk[4 * k + 1]),
-                         "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3]) : "memory");
+            for (int i = 0; i < 32; ++i) mx = (i < nv) ? fmaxf(mx, __uint_as_float(v[i])) : mx;
           }
         };
-        for (int c = 0; c < nfull; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + c * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
+        chunk_max(0, v0);
+        chunk_max(1, v1);
+        chunk_max(2, v2);
+        chunk_max(3, v3);
+        if (wq == 0 && lane == 0) trace(1 + t, 30 + j);
+        const float m_blk = mx * scale_log2;
+        // lazy reference update: exact as long as every exponent stays <= 2^8 above the reference
+        float alpha = 1.0f;
+        const bool need = m_blk > m_ref + 8.0f;
+        if (need) { alpha = ex2_approx(m_ref - m_blk); m_ref = m_blk; l_run *= alpha; }   // first block: alpha = 0, l = 0
+        if (j > 0) {
+          mbar_wait(pv_full(t), pvc & 1u);                                // PV(j-1) retired: P buffer free, O_t complete
+          ++pvc;
+          if (__any_sync(0xffffffffu, need)) {
+            tcgen05_fence_after();
+            const f32x2 a2 = splat2(alpha);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x0, x1;
-            unpack2(fma2(pack2u(v[2 * i], v[2 * i + 1]), sc2, nm2), x0, x1);
-            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            rsum2 = add2(rsum2, pack2(p0, p1));
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-          store_chunk(c, pk);
-        }
-        if (ntail) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tS + nfull * 32, v);
-          tmem_ld_wait();
-          uint32_t pk[16];
+            for (int g = 0; g < 4; ++g) {
+              uint32_t ov[16];
+              tmem_ld_32x32b_x16(tPV + g * 16, ov);
+              tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x0, x1;
-            unpack2(fma2(pack2u(v[2 * i], v[2 * i + 1]), sc2, nm2), x0, x1);
-            float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-            p0 = (2 * i < ntail) ? p0 : 0.f;
-            p1 = (2 * i + 1 < ntail) ? p1 : 0.f;
-            rsum2 = add2(rsum2, pack2(p0, p1));
-            pk[i] = pack_bf16x2(p0, p1);
+              for (int i = 0; i < 8; ++i) {
+                float x0, x1;
+                unpack2(mul2(pack2u(ov[2 * i], ov[2 * i + 1]), a2), x0, x1);
+                ov[2 * i] = __float_as_uint(x0);
+                ov[2 * i + 1] = __float_as_uint(x1);
+              }
+              tmem_st_32x32b_x16(tPV + g * 16, ov);
+            }
+            tmem_st_wait();
           }
-          store_chunk(nfull, pk);
         }
+        if (wq == 0 && lane == 0) trace(1 + t, 40 + j);
+        // probabilities -> bf16 -> swizzled shared memory (A operand of the PV product)
+        f32x2 rsum2 = 0ull;
+        const f32x2 sc2 = splat2(scale_log2), nm2 = splat2(-m_ref);
+        auto emit = [&](int c, const uint32_t (&v)[32]) {                 // chunk c = keys [32c, 32c+32) of the block
+          const int nv = valid - c * 32;
+          if (nv <= 0) return;                                            // beyond what the PV product reads
+          const uint32_t rowp = sPt + (c >> 1) * TILE_BYTES;
+          if (nv >= 32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int e = k * 8 + 2 * i;
+                float x0, x1;
+                unpack2(fma2(pack2u(v[e], v[e + 1]), sc2, nm2), x0, x1);
+                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                rsum2 = add2(rsum2, pack2(p0, p1));
+                pk[i] = pack_bf16x2(p0, p1);
+              }
+              const uint32_t slot = static_cast<uint32_t>(((c & 1) * 4 + k) ^ (row_local & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                           "r"(pk[3]) : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int e = k * 8 + 2 * i;
+                float x0, x1;
+                unpack2(fma2(pack2u(v[e], v[e + 1]), sc2, nm2), x0, x1);
+                const float p0 = (e < nv) ? ex2_approx(x0) : 0.f;
+                const float p1 = (e + 1 < nv) ? ex2_approx(x1) : 0.f;
+                rsum2 = add2(rsum2, pack2(p0, p1));
+                pk[i] = pack_bf16x2(p0, p1);
+              }
+              const uint32_t slot = static_cast<uint32_t>(((c & 1) * 4 + k) ^ (row_local & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                           "r"(pk[3]) : "memory");
+            }
+          }
+        };
+        if (j == 0) {                                                     // previous item's output slab (same bytes) must be drained
+          if (lane == 0) bulk_wait_group_read<0>();
+          __syncwarp();
+        }
+        emit(0, v0);
+        emit(1, v1);
+        emit(2, v2);
+        emit(3, v3);
         float rs0, rs1;
         unpack2(rsum2, rs0, rs1);
-        l_run = fmaf(l_run, alpha, rs0 + rs1);
-        m_run = m_new;
-        alpha_prev = alpha;
+        l_run += rs0 + rs1;
         tcgen05_fence_before();
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(s_empty(t)); mbar_arrive(p_full(t)); }
+        if (lane == 0) mbar_arrive(p_full(t));
+        if (wq == 0 && lane == 0) trace(1 + t, 50 + j);
       }
       mbar_wait(pv_full(t), pvc & 1u);
+      if (wq == 0 && lane == 0) trace(1 + t, 60);
       ++pvc;
       tcgen05_fence_after();
-      const float l_tot = l_run + exchange(xpar, l_run);                  // both halves of the row
-      xpar ^= 1u;
-      const float inv_l = 1.0f / l_tot;
-      const int row = q0 + row_local;
-      __nv_bfloat16* orow = out + (static_cast<size_t>(b) * nq + row) * ldo + h * DH + hf * 32;
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tPV, v);
-      tmem_ld_wait();
-      if (row < nq) {
-        const f32x2 a2 = splat2(alpha_prev), il2 = splat2(inv_l);
+      const f32x2 il2 = splat2(1.0f / l_run);
+      // normalised row -> this warp's 32-row slab of the (now idle) P buffer -> TMA store in 'b n (h d)' order;
+      // rows past nq are clipped by the tensor map
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t ov[32];
+        tmem_ld_32x32b_x32(tPV + c * 32, ov);
+        tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           uint32_t pk[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int d = k * 4 + i;                                          // pair index: dims 2d, 2d+1
-            pk[i] = pack_bf16x2_from(mul2(fma2(o[d], a2, pack2u(v[2 * d], v[2 * d + 1])), il2));
+            const int d = k * 4 + i;                                          // pair index within this half
+            pk[i] = pack_bf16x2_from(mul2(pack2u(ov[2 * d], ov[2 * d + 1]), il2));
           }
-          *reinterpret_cast<uint4*>(orow + k * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          const uint32_t slot = static_cast<uint32_t>((c * 4 + k) ^ (row_local & 7));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                       "r"(pk[3]) : "memory");
         }
       }
       tcgen05_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tmap_o, sP + t * P_BYTES + wq * 4096, h * DH, q0 + wq * 32, b);
+        bulk_commit_group();
+      }
+      __syncwarp();
+      if (wq == 0 && lane == 0) trace(1 + t, 70);
     }
+    if (lane == 0) bulk_wait_group<0>();      // output bytes globally visible before exit
   }
-
+done:
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -323,8 +402,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-struct AttnPlan { CUtensorMap q, k, v; };
-using AttnKey = std::tuple<const void*, int, const void*, int, const void*, int, int, int, int, int>;
+}  // namespace
+long long*& attn_trace_buffer() {   // device buffer [4 roles][256 (tag, clock) pairs]; null = tracing off
+  static long long* p = nullptr;
+  return p;
+}
+namespace {
+struct AttnPlan { CUtensorMap q, k, v, o; };
+using AttnKey = std::tuple<const void*, int, const void*, int, const void*, int, const void*, int, int, int, int, int>;
 std::map<AttnKey, AttnPlan>& plan_cache() {
   static std::map<AttnKey, AttnPlan> c;
   return c;
@@ -345,7 +430,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
     VB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
     configured = true;
   }
-  AttnKey key{q, ldq, k, ldk, v, ldv, B, nq, nk, heads};
+  AttnKey key{q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads};
   auto& cache = plan_cache();
   auto it = cache.find(key);
   if (it == cache.end()) {
@@ -355,14 +440,15 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
     p.q = make_tmap_3d(q, inner, nq, B, static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(nq) * ldq * 2, DH, BQ, 1);
     p.k = make_tmap_3d(k, inner, nk, B, static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(nk) * ldk * 2, DH, BKV, 1);
     p.v = make_tmap_3d(v, inner, nk, B, static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(nk) * ldv * 2, DH, BKV, 1);
+    p.o = make_tmap_3d(out, inner, nq, B, static_cast<uint64_t>(ldo) * 2, static_cast<uint64_t>(nq) * ldo * 2, DH, 32, 1);
     it = cache.emplace(key, p).first;
   }
   const int pairs = (nq + 2 * BQ - 1) / (2 * BQ);
   const int num_items = B * heads * pairs;
   const int grid = num_items < sm_count() ? num_items : sm_count();
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(it->second.q, it->second.k, it->second.v, out, ldo, heads, nq, nk, num_items,
-                                                     scale_log2);
+  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(it->second.q, it->second.k, it->second.v, it->second.o, heads, nq, nk, num_items,
+                                                     scale_log2, attn_trace_buffer());
   VB_CUDA(cudaGetLastError());
   count_launch();
   return true;

@@ -12,6 +12,7 @@
 
 #include <array>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -135,7 +136,7 @@ struct vb_handle {
   long long last_launches = 0;
 
   // optional per-kernel-class timing: CUDA events recorded on the launch stream around each call
-  enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_EMBED = 3, PROF_OTHER = 4, PROF_NUM = 5 };
+  enum { PROF_GEMM = 0, PROF_ATTN = 1, PROF_LN = 2, PROF_EMBED = 3, PROF_OTHER = 4, PROF_GEMM_GELU = 5, PROF_GEMM_RES = 6, PROF_NUM = 7 };
   struct ProfRec { int cls; cudaEvent_t a, b; double flops; double bytes; };
   bool profiling = false;
   std::vector<ProfRec> prof_recs;
@@ -677,7 +678,7 @@ void vb_handle::linear<__nv_bfloat16>(const __nv_bfloat16* A, int lda, int M, co
   const bool folded = L.ln_c1 != nullptr;
   VB_CHECK(!folded || (fast && e.ln_rows != nullptr), "internal: LayerNorm-folded Dense needs the tcgen05 path and row statistics");
   VB_CHECK(e.stats_out == nullptr || fast, "internal: row statistics requested from a non-tcgen05 GEMM");
-  ProfScope ps(this, fast ? PROF_GEMM : PROF_OTHER, 2.0 * M * L.N * K,
+  ProfScope ps(this, !fast ? PROF_OTHER : e.gelu ? PROF_GEMM_GELU : res ? PROF_GEMM_RES : PROF_GEMM, 2.0 * M * L.N * K,
                2.0 * (static_cast<double>(M) * K + static_cast<double>(L.N) * K + static_cast<double>(M) * L.N * (res ? 2 : 1)), s);
   if (fast) {
     PlanKey key{};
@@ -1043,6 +1044,22 @@ int vb_op_attention(int32_t precision, int32_t variant, const float* q, const fl
       dO.ensure(cq * sizeof(T));
       T* o_d = static_cast<T*>(dO.p);
       dS.ensure(static_cast<size_t>(B) * heads * nq * nk * 4);
+      DevMem dTrace;
+      const char* trace_path = getenv("VB_ATTN_TRACE");
+      if (trace_path) { dTrace.ensure(4 * 512 * 8); VB_CUDA(cudaMemset(dTrace.p, 0, 4 * 512 * 8)); attn_trace_buffer() = static_cast<long long*>(dTrace.p); }
+      struct TraceOff { ~TraceOff() { attn_trace_buffer() = nullptr; } } trace_off;
+      if (trace_path) {   // one traced launch, dumped as text: role tag clock
+        attention_fast<T>(q_d, inner, k_d, inner, v_d, inner, o_d, inner, B, nq, nk, heads, dim_head, variant, ma, mb, g, bt, 0);
+        VB_CUDA(cudaDeviceSynchronize());
+        std::vector<long long> h(4 * 512);
+        VB_CUDA(cudaMemcpy(h.data(), dTrace.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        attn_trace_buffer() = nullptr;
+        if (FILE* f = fopen(trace_path, "w")) {
+          for (int r = 0; r < 4; ++r)
+            for (int i = 0; i < 250 && h[r * 512 + 2 * i + 1] != 0; ++i) fprintf(f, "%d %lld %lld\n", r, h[r * 512 + 2 * i], h[r * 512 + 2 * i + 1]);
+          fclose(f);
+        }
+      }
       timed(iters, elapsed_ms, [&] {
         if (!attention_fast<T>(q_d, inner, k_d, inner, v_d, inner, o_d, inner, B, nq, nk, heads, dim_head, variant, ma, mb, g, bt, 0))
           attention_generic<T>(q_d, inner, k_d, inner, v_d, inner, o_d, inner, static_cast<float*>(dS.p), B, nq, nk, heads,

@@ -126,8 +126,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (warp-uniform loop, one elected lane issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
@@ -137,25 +137,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_stage0 + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          if (CG == 2) {
-            // both CTAs' bytes are counted on the leader's barrier, which expects the pair's total
-            const uint32_t lbar = full_bar(stage) & kPeerBitMask;
-            if (leader) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
-            tma_load_2d_cg2(sa, &tmap_a, lbar, kb * BK, m0);
-            tma_load_2d_cg2(sb, &tmap_b, lbar, kb * BK, n0);
-          } else {
-            mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);
-            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+          if (elect_one()) {
+            if (CG == 2) {
+              // both CTAs' bytes are counted on the leader's barrier, which expects the pair's total
+              const uint32_t lbar = full_bar(stage) & kPeerBitMask;
+              if (leader) mbar_arrive_expect_tx(full_bar(stage), CG * C::STAGE_BYTES);
+              tma_load_2d_cg2(sa, &tmap_a, lbar, kb * BK, m0);
+              tma_load_2d_cg2(sb, &tmap_b, lbar, kb * BK, n0);
+            } else {
+              mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);
+              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+            }
           }
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0 && leader) {
+    // ===================================================================== MMA issuer (leader CTA; warp-uniform loop)
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
+      const uint64_t da0 = make_smem_desc(smem_stage0, 16, 1024, 2);
+      const uint64_t db0 = make_smem_desc(smem_stage0 + C::A_BYTES, 16, 1024, 2);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -167,22 +172,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_stage0 + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t da = make_smem_desc(sa, 16, 1024, 2);
-          const uint64_t db = make_smem_desc(sb, 16, 1024, 2);
+          const uint64_t da = da0 + static_cast<uint32_t>(stage * (C::STAGE_BYTES >> 4));
+          const uint64_t db = db0 + static_cast<uint32_t>(stage * (C::STAGE_BYTES >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the 16-byte address field
-            if (CG == 2) umma_f16_ss_cg2(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the 16-byte address field
+              if (CG == 2) umma_f16_ss_cg2(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16_ss(tmem_d, da + 2u * k, db + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs) when these MMAs retire
+            if (CG == 2) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+            // accumulator complete -> epilogue warps of both CTAs
+            if (kb == num_kb - 1) { if (CG == 2) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc)); }
           }
-          // frees the smem stage (in both CTAs) when these MMAs retire
-          if (CG == 2) umma_commit_cg2(empty_bar(stage), 3); else umma_commit(empty_bar(stage));
+          __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete -> epilogue warps of both CTAs
-        if (CG == 2) umma_commit_cg2(tfull_bar(acc), 3); else umma_commit(tfull_bar(acc));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

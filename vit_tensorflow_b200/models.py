@@ -190,7 +190,7 @@ class _EngineModel:
                                                out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
         return out
 
-    PROFILE_CLASSES = ("gemm_tcgen05", "attention", "layernorm", "im2col", "other")
+    PROFILE_CLASSES = ("gemm_tcgen05", "attention", "layernorm", "im2col", "other", "gemm_tcgen05_gelu", "gemm_tcgen05_residual")
 
     def profile(self, on=True):
         """Record CUDA events around every kernel class on the launch stream (for the roofline report)."""
