@@ -19,11 +19,25 @@ void attention_generic(const T* q, int ldq, const T* k, int ldk, const T* v, int
   attn_pv<T>(S, v, ldv, out, ldo, B, heads, nq, nk, dh, s);
 }
 
+template <>
+void attention_generic<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                                      __nv_bfloat16* out, int ldo, float* S, int B, int nq, int nk, int heads, int dh, int variant,
+                                      const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta,
+                                      cudaStream_t s) {
+  if (attention_generic_mma(q, ldq, k, ldk, v, ldv, out, ldo, S, B, nq, nk, heads, dh, variant, mix_a, mix_b, ln_gamma, ln_beta, s))
+    return;
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  attn_scores<__nv_bfloat16>(q, ldq, k, ldk, S, B, heads, nq, nk, dh, scale, s);
+  if (variant == 2) attn_head_mix(S, mix_a, nullptr, nullptr, B, heads, nq, nk, s);
+  attn_softmax(S, static_cast<long long>(B) * heads * nq, nk, s);
+  if (variant == 1) attn_head_mix(S, mix_a, ln_gamma, ln_beta, B, heads, nq, nk, s);
+  if (variant == 2) attn_head_mix(S, mix_b, nullptr, nullptr, B, heads, nq, nk, s);
+  attn_pv<__nv_bfloat16>(S, v, ldv, out, ldo, B, heads, nq, nk, dh, s);
+}
+
 template void attention_generic<float>(const float*, int, const float*, int, const float*, int, float*, int, float*, int, int, int,
                                        int, int, int, const float*, const float*, const float*, const float*, cudaStream_t);
-template void attention_generic<__nv_bfloat16>(const __nv_bfloat16*, int, const __nv_bfloat16*, int, const __nv_bfloat16*, int,
-                                               __nv_bfloat16*, int, float*, int, int, int, int, int, int, const float*,
-                                               const float*, const float*, const float*, cudaStream_t);
+
 
 template <>
 bool attention_fast<float>(const float*, int, const float*, int, const float*, int, float*, int, int, int, int, int, int, int,

@@ -5,18 +5,18 @@
 // The [b,h,n,n] score tensor the reference materialises twice in memory (dots, attn) lives only in tensor memory.
 // Persistent kernel, one CTA per SM, work item = (b, h, pair of 128-row query tiles); the two tiles of an item
 // share every K/V block and ping-pong between the tensor core and two softmax warpgroups:
-//   warp 0       TMA producer: Q tiles, then K/V blocks of 128 keys into a 3-stage ring, running ahead across
+//   warp 8       TMA producer: Q tiles, then K/V blocks of 128 keys into a 3-stage ring, running ahead across
 //                items.  Q, K and V are read straight out of the row-major projection output ([B, n, 3*h*dh] for
 //                the fused to_qkv) through 3-D tensor maps (box 64 x 128 x 1): the head split
 //                'b n (h d) -> b h n d' (vit.py:74) costs nothing, and rows past n are zero-filled by TMA instead
 //                of bleeding into the next image.
-//   warps 1, 2    MMA issuers, one per query tile (independent pipelines): S_t = Q_t K^T (128 x 128 x 64,
+//   warps 10, 11  MMA issuers, one per query tile (independent pipelines): S_t = Q_t K^T (128 x 128 x 64,
 //                K-major operands) into TMEM, O_t += P_t V (128 x 64 x 128; P K-major from shared memory, V MN-major
 //                exactly as TMA delivered it).  S(k+1) is issued BEFORE PV(k): the softmax group keeps S in
 //                registers, so the S buffer is free again long before P(k) is ready -- a clock64 trace of the
 //                single-issuer form (profiles/r01_attn_trace_v5.txt) showed the softmax groups waiting 1.6-2 K
 //                cycles per block for S and the issuer thread spending ~100 cycles per MMA on descriptor math.
-//   warps 4-7 / 8-11  softmax group of tile 0 / 1: thread i owns query row i of its tile (TMEM lane i).
+//   warps 0-3 / 4-7   softmax group of tile 0 / 1: thread i owns query row i of its tile (TMEM lane i).
 //                S is read from TMEM exactly ONCE per block (tcgen05.ld -> 128 registers: TMEM->register bandwidth,
 //                not MUFU, bounded the earlier two-pass forms -- see profiles/), the S buffer is released to the
 //                tensor core immediately, max / exp2 / sum run on registers with packed fp32x2 math, P goes as bf16
@@ -40,7 +40,8 @@ constexpr int BKV = 128;         // keys per block
 constexpr int KV_ST = 3;
 constexpr int TILE_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr int P_BYTES = 2 * TILE_BYTES;      // 128 rows x 128 keys bf16 as two 64-column swizzled blocks
-constexpr int ATT_THREADS = 384;             // warp 0 TMA, warps 1-2 MMA issuers, warp 3 idle, warps 4-7 / 8-11 softmax
+constexpr int ATT_THREADS = 384;             // warps 0-3 / 4-7 softmax of tile 0 / 1, warp 8 TMA, warps 10-11 MMA issuers
+constexpr int ATT_PRODUCER_WARP = 8, ATT_MMA_WARP0 = 10;   // issue arbiter favours high warp ids: issuers on top
 constexpr int SMEM_DATA = 2 * TILE_BYTES /*Q*/ + KV_ST * 2 * TILE_BYTES /*K,V*/ + 2 * P_BYTES;
 constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
@@ -80,12 +81,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int s = 0; s < KV_ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }   // one release per tile issuer
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
+  if (warp == ATT_MMA_WARP0) tmem_alloc<TMEM_COLS_ATT>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                 // prologue above overlapped the producer GEMM's tail; Q/K/V are complete from here on
+  pdl_launch_dependents();
   // optional timeline trace (VB_ATTN_TRACE=1 through vb_op_attention): CTA 0 records (tag, clock) pairs per role
   int dbg_n = 0;
   auto trace = [&](int role, int tag) {
@@ -96,7 +99,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   };
 
-  if (warp == 0) {
+  if (warp == ATT_PRODUCER_WARP) {
     // ===================================================================== TMA producer (warp-uniform loop, elected lane issues)
     {
       if (lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); }
@@ -128,10 +131,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp >= ATT_MMA_WARP0) {
     // ===================================================================== MMA issuer of tile t (warp-uniform loop)
     {
-      const int t = warp - 1;
+      const int t = warp - ATT_MMA_WARP0;
       const uint32_t tS_d = tmem_base + TM_S + t * 128, tO_d = tmem_base + TM_PV + t * 64;
       const uint64_t dq = make_smem_desc(sQ + t * TILE_BYTES, 16, 1024, 2);
       const uint64_t dk0 = make_smem_desc(sK, 16, 1024, 2);
@@ -219,8 +222,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else {
     // ===================================================================== softmax groups (4 warps per tile)
-    if (warp == 3) goto done;               // spare warp
-    const int t = (warp - 4) >> 2;          // tile slot
+    if (warp >= 8) goto done;               // spare warp 9
+    const int t = warp >> 2;                // tile slot
     const int wq = warp & 3;                // TMEM lane quarter this warp may access
     const int row_local = wq * 32 + lane;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
@@ -396,7 +399,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 done:
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == ATT_MMA_WARP0) {
     tcgen05_fence_after();
     tmem_dealloc<TMEM_COLS_ATT>(tmem_base);
   }
@@ -447,8 +450,18 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   const int num_items = B * heads * pairs;
   const int grid = num_items < sm_count() ? num_items : sm_count();
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
-  attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, s>>>(it->second.q, it->second.k, it->second.v, it->second.o, heads, nq, nk, num_items,
-                                                     scale_log2, attn_trace_buffer());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(ATT_THREADS);
+  cfg.dynamicSmemBytes = ATT_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, it->second.q, it->second.k, it->second.v, it->second.o, heads, nq, nk,
+                             num_items, scale_log2, attn_trace_buffer()));
   VB_CUDA(cudaGetLastError());
   count_launch();
   return true;

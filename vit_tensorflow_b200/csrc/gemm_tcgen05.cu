@@ -12,14 +12,16 @@
 // the leader CTA issues M = 256 MMAs that read B from both CTAs' shared memory.  Per SM this cuts the TMA-write +
 // UMMA-read shared-memory traffic from 192 to 128 B/clk -- the 1-CTA form measured 65 % tensor-pipe activity
 // (profiles/r01_ncu_gemm_qkv_1cta.txt), exactly the 128/192 shared-memory-bandwidth bound.
-//   warp 0      TMA producer: A tile 128x64 + B tile (BN/CG)x64 per k-block into a STAGES-deep 128B-swizzled ring
-//   warp 1      MMA issuer (leader CTA): one thread issues tcgen05.mma (128*CG x BN x 16) into a double-buffered
+//   warp 10     TMA producer: A tile 128x64 + B tile (BN/CG)x64 per k-block into a STAGES-deep 128B-swizzled ring
+//   warp 11     MMA issuer (leader CTA): one thread issues tcgen05.mma (128*CG x BN x 16) into a double-buffered
 //               TMEM accumulator (each CTA holds its 128 rows)
-//   warps 4-11  epilogue: tcgen05.ld -> bias/GELU/LayerScale/residual in registers -> bf16 -> per-warp swizzled smem
+//   warps 0-7   epilogue: tcgen05.ld -> bias/GELU/LayerScale/residual in registers -> bf16 -> per-warp swizzled smem
 //               slab (8 x 4 KB) -> per-warp TMA store.  Runs concurrently with the next tile's main loop.
 #include "common.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
+
+#include <cstdlib>
 
 namespace vb {
 
@@ -29,7 +31,9 @@ constexpr int BM = 128;
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARP0 = 0;             // epilogue warps 0-7 (TMEM lane quarter = warp % 4)
+constexpr int PRODUCER_WARP = 10;        // the issue arbiter favours high warp ids: keep the two latency-critical
+constexpr int MMA_WARP = 11;             // single-instruction-stream roles above the math-heavy epilogue warps
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int STAGING_BYTES = 4096;       // per-warp slab: 32 rows x 64 bf16 columns (128-byte swizzled rows)
 constexpr int NUM_STAGING = 8;
@@ -69,13 +73,57 @@ __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
   return fma2(abs2(h), erf_abs, h);                                    // 0.5x + 0.5|x|erf(|x|/sqrt2)
 }
 
+// Same GELU with erf from Abramowitz-Stegun 7.1.28, erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16 (|err| <= 3e-7):
+// ONE MUFU (rcp) per element instead of two (rcp + ex2) at the price of two more FMA-pipe pair instructions.
+__device__ __forceinline__ f32x2 gelu_erf2_rcp16(f32x2 x) {
+  const f32x2 ax = abs2(x);
+  const f32x2 z = mul2(ax, splat2(0.70710678118654752440f));
+  f32x2 p = fma2(splat2(0.0000430638f), z, splat2(0.0002765672f));
+  p = fma2(p, z, splat2(0.0001520143f));
+  p = fma2(p, z, splat2(0.0092705272f));
+  p = fma2(p, z, splat2(0.0422820123f));
+  p = fma2(p, z, splat2(0.0705230784f));
+  p = fma2(p, z, splat2(1.0f));
+  p = mul2(p, p);
+  p = mul2(p, p);
+  p = mul2(p, p);
+  p = mul2(p, p);                                                      // overflow -> inf -> rcp = 0 -> erf = 1
+  float d0, d1;
+  unpack2(p, d0, d1);
+  const f32x2 r = pack2(rcp_approx(d0), rcp_approx(d1));
+  const f32x2 h = mul2(x, splat2(0.5f));
+  const f32x2 ah = abs2(h);
+  return fma2(ah, add2(splat2(1.0f), r ^ 0x8000000080000000ull), h);   // 0.5x + 0.5|x|(1 - r)
+}
+
+// Three-term variant, Abramowitz-Stegun 7.1.25 (|err| <= 2.5e-5: at most 0.08 bf16 ulp on the GELU output, measured
+// in tools/gelu_error.py): two FFMA2 fewer per pair than 7.1.26.
+__device__ __forceinline__ f32x2 gelu_erf2_3term(f32x2 x) {
+  const f32x2 ax = abs2(x);
+  const f32x2 z = mul2(ax, splat2(0.70710678118654752440f));
+  const f32x2 den = fma2(splat2(0.47047f), z, splat2(1.0f));
+  float d0, d1;
+  unpack2(den, d0, d1);
+  const f32x2 t = pack2(rcp_approx(d0), rcp_approx(d1));
+  f32x2 p = fma2(splat2(-0.7478556f), t, splat2(0.0958798f));          // coefficients negated: p = -poly(t)
+  p = fma2(p, t, splat2(-0.3480242f));
+  p = mul2(p, t);
+  const f32x2 zz = mul2(mul2(z, z), splat2(-1.4426950408889634f));
+  float e0, e1;
+  unpack2(zz, e0, e1);
+  const f32x2 e = pack2(ex2_approx(e0), ex2_approx(e1));
+  const f32x2 erf_abs = fma2(p, e, splat2(1.0f));
+  const f32x2 h = mul2(x, splat2(0.5f));
+  return fma2(abs2(h), erf_abs, h);
+}
+
 template <int BN, bool GELU, bool RES, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* __restrict__ ln_rows,
-                 float2* __restrict__ stats_out, int stats_parts) {
+                 float2* __restrict__ stats_out, int stats_parts, int gelu_mode) {
   using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -102,7 +150,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int tile0 = blockIdx.x / CG;                               // persistent schedule over clusters
   const int tile_step = gridDim.x / CG;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
@@ -116,16 +164,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     if (CG == 2) tmem_alloc_cg2<C::TMEM_COLS>(tmem_ptr_smem); else tmem_alloc<C::TMEM_COLS>(tmem_ptr_smem);
   }
   tcgen05_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();                                 // peer barriers are initialised before any remote signal
   tcgen05_fence_after();
+  // Everything above overlapped the previous kernel's tail (PDL); from here on we touch its outputs.
+  pdl_wait();
+  pdl_launch_dependents();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // ===================================================================== TMA producer (warp-uniform loop, one elected lane issues)
     {
       int stage = 0;
@@ -155,7 +206,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ===================================================================== MMA issuer (leader CTA; warp-uniform loop)
     if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(TM, BN, 0, 0);
@@ -192,7 +243,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else if (warp < EPI_WARP0 + NUM_EPI_THREADS / 32) {
     // ===================================================================== epilogue (8 warps)
     // Warp (q, hf) owns accumulator rows [32q, 32q+32) (its TMEM lane quarter) and the column half hf of the tile,
     // 64 columns (one 128-byte swizzled row) at a time, with a private 4 KB staging slab and its own TMA stores:
@@ -271,8 +322,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
             if (GELU) {
+              if (gelu_mode == 0) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
+                for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
+              } else if (gelu_mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = gelu_erf2_rcp16(f[j]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = gelu_erf2_3term(f[j]);
+              }
             }
             if (scale != nullptr) {
               const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(scale + ncol);
@@ -340,7 +399,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tcgen05_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();     // no CTA exits (or frees TMEM) while its peer can still signal / read it
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     tcgen05_fence_after();
     if (CG == 2) tmem_dealloc_cg2<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
@@ -362,6 +421,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int gelu_mode() {   // VB_GELU_MODE=0: A-S 7.1.26 (rcp + ex2); 1: A-S 7.1.28 (rcp only); 2: A-S 7.1.25 (3 terms).  A/B switch.
+  static int m = -1;
+  if (m < 0) { const char* e = getenv("VB_GELU_MODE"); m = e ? atoi(e) : 0; }
+  return m;
+}
+
 template <int BN, bool GELU, bool RES, int CG>
 void launch(const GemmBf16& g, cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, GELU, RES, CG>;
@@ -375,15 +440,17 @@ void launch(const GemmBf16& g, cudaStream_t stream) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
-                             reinterpret_cast<const float2*>(g.ln_rows), reinterpret_cast<float2*>(g.stats_out), g.stats_parts));
+                             reinterpret_cast<const float2*>(g.ln_rows), reinterpret_cast<float2*>(g.stats_out), g.stats_parts, gelu_mode()));
   count_launch();
 }
 

@@ -513,6 +513,8 @@ __global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, f
 }
 
 __global__ void row_stats_finalize_kernel(const float2* __restrict__ stats, float2* __restrict__ rows, int M, int parts, float inv_d) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");                 // PDL: the producer GEMM's statistics are complete
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // single wave: let the consumer GEMM start its prologue
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   const float2* p = stats + static_cast<long long>(m) * parts;
@@ -661,9 +663,18 @@ void ln_fold_consts(const float* W, const __nv_bfloat16* Wt, int ldw, const floa
 }
 
 void row_stats_finalize(const float* stats, float* rows, int M, int parts, int D, cudaStream_t s) {
-  row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, s>>>(reinterpret_cast<const float2*>(stats), reinterpret_cast<float2*>(rows), M,
-                                                          parts, 1.0f / static_cast<float>(D));
-  VB_LAUNCHED();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((M + 255) / 256);
+  cfg.blockDim = dim3(256);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA(cudaLaunchKernelEx(&cfg, row_stats_finalize_kernel, reinterpret_cast<const float2*>(stats), reinterpret_cast<float2*>(rows), M,
+                             parts, 1.0f / static_cast<float>(D)));
+  count_launch();
 }
 
 void row_stats_bf16(const __nv_bfloat16* X, int ldx, float* stats, int M, int D, cudaStream_t s) {

@@ -49,6 +49,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor is still running; pdl_wait() blocks until every prerequisite grid has completed and its
+// memory is visible, pdl_launch_dependents() lets the next kernel in the stream begin its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // One lane of a fully converged warp (elect.sync): lets the surrounding loop stay warp-uniform so that addresses,
 // descriptors and coordinates live in uniform registers (a lane-0-only loop makes ptxas emit R2UR waterfall loops
 // around every UTCHMMA / UTMALDG).
