@@ -64,5 +64,6 @@ GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt
                         bool gelu);
 void gemm_bf16_run(const GemmBf16& g, cudaStream_t stream);
 bool gemm_bf16_supported(int M, int N, int K, int lda, int ldw, int ldc);
+long long*& gemm_trace_buffer();
 
 }  // namespace vb

@@ -36,17 +36,18 @@ constexpr int PRODUCER_WARP = 10;        // the issue arbiter favours high warp 
 constexpr int MMA_WARP = 11;             // single-instruction-stream roles above the math-heavy epilogue warps
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int STAGING_BYTES = 4096;       // per-warp slab: 32 rows x 64 bf16 columns (128-byte swizzled rows)
-constexpr int NUM_STAGING = 8;
+constexpr int NUM_STAGING = 8;            // one 4 KB slab per epilogue warp
+constexpr int CONST_BYTES = 2 * 3 * 256 * 4;  // per-column epilogue constants (bias/c2, c1, scale) of a tile, double-buffered
 
 template <int BN, int CG>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;               // each CTA of a pair stages half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - 256 - 1024) / STAGE_BYTES;
+  static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - CONST_BYTES - 256 - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 256 or 512)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STAGING * STAGING_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STAGING * STAGING_BYTES + CONST_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 };
 
 // Exact-erf GELU (vit.py:34) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-exact for a
@@ -73,63 +74,20 @@ __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
   return fma2(abs2(h), erf_abs, h);                                    // 0.5x + 0.5|x|erf(|x|/sqrt2)
 }
 
-// Same GELU with erf from Abramowitz-Stegun 7.1.28, erf(z) = 1 - (1 + a1 z + ... + a6 z^6)^-16 (|err| <= 3e-7):
-// ONE MUFU (rcp) per element instead of two (rcp + ex2) at the price of two more FMA-pipe pair instructions.
-__device__ __forceinline__ f32x2 gelu_erf2_rcp16(f32x2 x) {
-  const f32x2 ax = abs2(x);
-  const f32x2 z = mul2(ax, splat2(0.70710678118654752440f));
-  f32x2 p = fma2(splat2(0.0000430638f), z, splat2(0.0002765672f));
-  p = fma2(p, z, splat2(0.0001520143f));
-  p = fma2(p, z, splat2(0.0092705272f));
-  p = fma2(p, z, splat2(0.0422820123f));
-  p = fma2(p, z, splat2(0.0705230784f));
-  p = fma2(p, z, splat2(1.0f));
-  p = mul2(p, p);
-  p = mul2(p, p);
-  p = mul2(p, p);
-  p = mul2(p, p);                                                      // overflow -> inf -> rcp = 0 -> erf = 1
-  float d0, d1;
-  unpack2(p, d0, d1);
-  const f32x2 r = pack2(rcp_approx(d0), rcp_approx(d1));
-  const f32x2 h = mul2(x, splat2(0.5f));
-  const f32x2 ah = abs2(h);
-  return fma2(ah, add2(splat2(1.0f), r ^ 0x8000000080000000ull), h);   // 0.5x + 0.5|x|(1 - r)
-}
-
-// Three-term variant, Abramowitz-Stegun 7.1.25 (|err| <= 2.5e-5: at most 0.08 bf16 ulp on the GELU output, measured
-// in tools/gelu_error.py): two FFMA2 fewer per pair than 7.1.26.
-__device__ __forceinline__ f32x2 gelu_erf2_3term(f32x2 x) {
-  const f32x2 ax = abs2(x);
-  const f32x2 z = mul2(ax, splat2(0.70710678118654752440f));
-  const f32x2 den = fma2(splat2(0.47047f), z, splat2(1.0f));
-  float d0, d1;
-  unpack2(den, d0, d1);
-  const f32x2 t = pack2(rcp_approx(d0), rcp_approx(d1));
-  f32x2 p = fma2(splat2(-0.7478556f), t, splat2(0.0958798f));          // coefficients negated: p = -poly(t)
-  p = fma2(p, t, splat2(-0.3480242f));
-  p = mul2(p, t);
-  const f32x2 zz = mul2(mul2(z, z), splat2(-1.4426950408889634f));
-  float e0, e1;
-  unpack2(zz, e0, e1);
-  const f32x2 e = pack2(ex2_approx(e0), ex2_approx(e1));
-  const f32x2 erf_abs = fma2(p, e, splat2(1.0f));
-  const f32x2 h = mul2(x, splat2(0.5f));
-  return fma2(abs2(h), erf_abs, h);
-}
-
 template <int BN, bool GELU, bool RES, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* __restrict__ ln_rows,
-                 float2* __restrict__ stats_out, int stats_parts, int gelu_mode) {
+                 float2* __restrict__ stats_out, int stats_parts, long long* __restrict__ dbg) {
   using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stage0 = smem_base;
   const uint32_t smem_staging = smem_base + C::STAGES * C::STAGE_BYTES;
-  const uint32_t bar_base = smem_staging + NUM_STAGING * STAGING_BYTES;
+  const uint32_t smem_consts = smem_staging + NUM_STAGING * STAGING_BYTES;
+  const uint32_t bar_base = smem_consts + CONST_BYTES;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
@@ -174,6 +132,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // Everything above overlapped the previous kernel's tail (PDL); from here on we touch its outputs.
   pdl_wait();
   pdl_launch_dependents();
+  // optional timeline trace (VB_GEMM_TRACE=path through vb_op_linear): CTA 0 records (tag, clock) pairs per role
+  int dbg_n = 0;
+  auto trace = [&](int role, int tag) {
+    if (dbg != nullptr && blockIdx.x == 0 && dbg_n < 250) {
+      dbg[role * 512 + 2 * dbg_n] = tag;
+      dbg[role * 512 + 2 * dbg_n + 1] = clock64();
+      ++dbg_n;
+    }
+  };
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_smem - smem_base));
 
   if (warp == PRODUCER_WARP) {
@@ -217,8 +184,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
+        if (lane == 0) trace(0, 1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);   // epilogue has drained this accumulator buffer
         tcgen05_fence_after();
+        if (lane == 0) trace(0, 2);
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
@@ -240,6 +209,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
+        if (lane == 0) trace(0, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -254,6 +224,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int row_local = q * 32 + lane;
     const uint32_t slab = smem_staging + e * 4096;                 // 32 rows x 128 bytes, 1024-aligned
     const uint32_t srow = slab + lane * 128;
+    const int etid = threadIdx.x - EPI_WARP0 * 32;                 // 0..255: one tile column per epilogue thread
     constexpr int CHUNKS = BN / 128;                               // 64-column chunks per warp per tile
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -274,115 +245,126 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int rn = ((t + tile_step) / tiles_n) * TM + cta_rank * BM + row_local;
         if (rn < M) ln_next = ln_rows[rn];
       }
+      // Stage this tile's per-column constants in shared memory (one column per thread, coalesced); the chunk loop then
+      // reads them as broadcast LDS instead of exposing a global-load round trip per 16 columns (clock64 traces showed
+      // ~1.3 K cycles per 16-column group with __ldg constants, whatever the epilogue math).
+      const uint32_t cbase = smem_consts + acc * (3 * 256 * 4);
+      {
+        const int n = n0 + etid;
+        float cb = 0.f, c1v = 0.f, sc = 1.f;
+        if (etid < BN && n < N) {
+          if (bias != nullptr) cb = __ldg(bias + n);
+          if (ln_c1 != nullptr) c1v = __ldg(ln_c1 + n);
+          if (scale != nullptr) sc = __ldg(scale + n);
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbase + etid * 4), "f"(cb) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbase + 1024 + etid * 4), "f"(c1v) : "memory");
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbase + 2048 + etid * 4), "f"(sc) : "memory");
+      }
+      named_bar_sync(1, NUM_EPI_THREADS);
+      if (lane == 0 && q == 0) trace(1 + hf, 10);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
+      if (lane == 0 && q == 0) trace(1 + hf, 11);
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
-        const int ncol0 = n0 + (hf * CHUNKS + c) * 64;
+        const int cc = hf * CHUNKS + c;                             // 64-column chunk of the tile
+        const int ncol0 = n0 + cc * 64;
         const bool col_ok = ncol0 < N;                              // N % 64 == 0: a chunk is entirely in or out
-        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + (hf * CHUNKS + c) * 64;
-        uint32_t packed[32];                                        // 64 bf16 outputs of this thread's row
+        const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cc * 64;
+        // residual row segment (128 bytes) and all four TMEM loads of the chunk are issued up front
+        uint4 rres[8];
+        const bool res_ok = RES && col_ok && row < M;
+        if (RES) {
+          const uint4* rp = reinterpret_cast<const uint4*>(res + (res_ok ? static_cast<size_t>(row) * ldr + ncol0 : 0));
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int ncol = ncol0 + half * 32;
-          uint4 rres[4];
-          if (RES) {
-            if (col_ok && row < M) {
-              const uint4* rp = reinterpret_cast<const uint4*>(res + static_cast<size_t>(row) * ldr + ncol);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) rres[k] = rp[k];
-            } else {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) rres[k] = make_uint4(0, 0, 0, 0);
-            }
-          }
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tcol + half * 32, v);
-          tmem_ld_wait();
-          f32x2 f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = pack2u(v[2 * j], v[2 * j + 1]);
-          if (col_ok) {
-            if (ln_c1 != nullptr) {
-              const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(ln_c1 + ncol);
-              const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const ulonglong2 c4 = __ldg(cp + k), b4 = __ldg(bp + k);
-                f[2 * k + 0] = fma2(f[2 * k + 0], ln_rstd2, fma2(c4.x, ln_nmr2, b4.x));
-                f[2 * k + 1] = fma2(f[2 * k + 1], ln_rstd2, fma2(c4.y, ln_nmr2, b4.y));
-              }
-            } else if (bias != nullptr) {
-              const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const ulonglong2 b4 = __ldg(bp + k);
-                f[2 * k + 0] = add2(f[2 * k + 0], b4.x);
-                f[2 * k + 1] = add2(f[2 * k + 1], b4.y);
-              }
-            }
-            if (GELU) {
-              if (gelu_mode == 0) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = gelu_erf2(f[j]);
-              } else if (gelu_mode == 1) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = gelu_erf2_rcp16(f[j]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = gelu_erf2_3term(f[j]);
-              }
-            }
-            if (scale != nullptr) {
-              const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(scale + ncol);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const ulonglong2 s4 = __ldg(sp + k);
-                f[2 * k + 0] = mul2(f[2 * k + 0], s4.x);
-                f[2 * k + 1] = mul2(f[2 * k + 1], s4.y);
-              }
-            }
-            if (RES) {
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t w4[4] = {rres[k].x, rres[k].y, rres[k].z, rres[k].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) f[4 * k + i] = add2(f[4 * k + i], bf16x2_to_f32x2(w4[i]));
-              }
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) packed[half * 16 + j] = pack_bf16x2_from(f[j]);
+          for (int k = 0; k < 8; ++k) rres[k] = res_ok ? rp[k] : make_uint4(0, 0, 0, 0);
         }
-        // (sum, sum of squares) of this row's 64 stored bf16 outputs: LayerNorm statistics for the consumer GEMM
-        if (stats_out != nullptr && col_ok && row < M) {
-          f32x2 s1 = 0ull, s2 = 0ull;
+        uint32_t v[4][16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const f32x2 ab = bf16x2_to_f32x2(packed[j]);
-            s1 = add2(s1, ab);
-            s2 = fma2(ab, ab, s2);
-          }
-          float a0, a1, b0, b1;
-          unpack2(s1, a0, a1);
-          unpack2(s2, b0, b1);
-          stats_out[static_cast<size_t>(row) * stats_parts + (ncol0 >> 6)] = make_float2(a0 + a1, b0 + b1);
-        }
+        for (int g = 0; g < 4; ++g) tmem_ld_32x32b_x16(tcol + g * 16, v[g]);
+        tmem_ld_wait();
+        if (lane == 0 && q == 0) trace(1 + hf, 30 + c);
         // the slab must have been fully read by this warp's previous TMA store
         if (lane == 0) bulk_wait_group_read<0>();
         __syncwarp();
+        if (lane == 0 && q == 0) trace(1 + hf, 40 + c);
+        f32x2 st1 = 0ull, st2 = 0ull;                               // (sum, sum of squares) of the stored bf16 outputs
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t slot = static_cast<uint32_t>(k ^ (lane & 7));   // 128B swizzle: 16-byte slot ^ (row % 8)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + slot * 16), "r"(packed[4 * k]),
-                       "r"(packed[4 * k + 1]), "r"(packed[4 * k + 2]), "r"(packed[4 * k + 3]) : "memory");
+        for (int g = 0; g < 4; ++g) {
+          const uint32_t coff = cbase + (cc * 64 + g * 16) * 4;
+          f32x2 f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = pack2u(v[g][2 * j], v[g][2 * j + 1]);
+          if (ln_c1 != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              f32x2 c0, c1p, b0, b1;
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1p) : "r"(coff + 1024 + k * 16));
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(coff + k * 16));
+              f[2 * k + 0] = fma2(f[2 * k + 0], ln_rstd2, fma2(c0, ln_nmr2, b0));
+              f[2 * k + 1] = fma2(f[2 * k + 1], ln_rstd2, fma2(c1p, ln_nmr2, b1));
+            }
+          } else if (bias != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              f32x2 b0, b1;
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(coff + k * 16));
+              f[2 * k + 0] = add2(f[2 * k + 0], b0);
+              f[2 * k + 1] = add2(f[2 * k + 1], b1);
+            }
+          }
+          if (GELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = gelu_erf2(f[j]);
+          }
+          if (scale != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              f32x2 s0, s1;
+              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(s0), "=l"(s1) : "r"(coff + 2048 + k * 16));
+              f[2 * k + 0] = mul2(f[2 * k + 0], s0);
+              f[2 * k + 1] = mul2(f[2 * k + 1], s1);
+            }
+          }
+          if (RES) {
+            const uint32_t w8[8] = {rres[2 * g].x, rres[2 * g].y, rres[2 * g].z, rres[2 * g].w,
+                                    rres[2 * g + 1].x, rres[2 * g + 1].y, rres[2 * g + 1].z, rres[2 * g + 1].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = add2(f[i], bf16x2_to_f32x2(w8[i]));
+          }
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = pack_bf16x2_from(f[j]);
+          if (stats_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const f32x2 ab = bf16x2_to_f32x2(pk[j]);
+              st1 = add2(st1, ab);
+              st2 = fma2(ab, ab, st2);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint32_t slot = static_cast<uint32_t>((g * 2 + k) ^ (lane & 7));   // 128B swizzle: 16-byte slot ^ (row % 8)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + slot * 16), "r"(pk[4 * k]), "r"(pk[4 * k + 1]),
+                         "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3]) : "memory");
+          }
         }
+        if (stats_out != nullptr && col_ok && row < M) {
+          float a0, a1, b0, b1;
+          unpack2(st1, a0, a1);
+          unpack2(st2, b0, b1);
+          stats_out[static_cast<size_t>(row) * stats_parts + (ncol0 >> 6)] = make_float2(a0 + a1, b0 + b1);
+        }
+        if (lane == 0 && q == 0) trace(1 + hf, 50 + c);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           if (col_ok) tma_store_2d(&tmap_c, slab, ncol0, m0 + q * 32);
           bulk_commit_group();
         }
+        if (lane == 0 && q == 0) trace(1 + hf, 20 + c);
       }
       // all TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld above)
       tcgen05_fence_before();
@@ -421,11 +403,12 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int gelu_mode() {   // VB_GELU_MODE=0: A-S 7.1.26 (rcp + ex2); 1: A-S 7.1.28 (rcp only); 2: A-S 7.1.25 (3 terms).  A/B switch.
-  static int m = -1;
-  if (m < 0) { const char* e = getenv("VB_GELU_MODE"); m = e ? atoi(e) : 0; }
-  return m;
+}  // namespace
+long long*& gemm_trace_buffer() {   // debugging aid: device trace buffer [3 roles][256 (tag, clock)]; null = off
+  static long long* p = nullptr;
+  return p;
 }
+namespace {
 
 template <int BN, bool GELU, bool RES, int CG>
 void launch(const GemmBf16& g, cudaStream_t stream) {
@@ -450,7 +433,7 @@ void launch(const GemmBf16& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
-                             reinterpret_cast<const float2*>(g.ln_rows), reinterpret_cast<float2*>(g.stats_out), g.stats_parts, gelu_mode()));
+                             reinterpret_cast<const float2*>(g.ln_rows), reinterpret_cast<float2*>(g.stats_out), g.stats_parts, gemm_trace_buffer()));
   count_launch();
 }
 

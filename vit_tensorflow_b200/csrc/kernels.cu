@@ -190,23 +190,25 @@ __global__ void layernorm_generic_kernel(const T* __restrict__ x, int ldx, const
 // ------------------------------------------------------------------------------------------ SIMT GEMM
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// 64x64 output tile, 16x16 threads x (4x4) micro-tile, BK = 16; exact fp32 FMA accumulation in k order.
-template <typename TA, typename TW, typename TO>
+// (16*TM)x64 output tile, 16x16 threads x (TM x 4) micro-tile, BK = 16; exact fp32 FMA accumulation in k order.
+// TM = 4: 64-row tiles; TM = 1: 16-row tiles for small-M problems (the classifier head) so the grid still fills the GPU.
+template <typename TA, typename TW, typename TO, int TM>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, int wsk, int wsn, TO* out, int ldc, int M, int N,
                  int K, const float* __restrict__ bias, const float* __restrict__ scale, const TO* res, int ldr, int gelu) {
-  __shared__ float As[16][64 + 1];
+  constexpr int BMT = 16 * TM;
+  __shared__ float As[16][BMT + 1];
   __shared__ float Ws[16][64 + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4];
+  const int m0 = blockIdx.y * BMT, n0 = blockIdx.x * 64;
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += 16) {
     for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      {  // A tile: consecutive threads along k (contiguous in memory)
+      if (e < 16 * BMT) {  // A tile: consecutive threads along k (contiguous in memory)
         const int kk = e & 15, mm = e >> 4;
         const int m = m0 + mm, k = k0 + kk;
         As[kk][mm] = (m < M && k < K) ? to_f(A[static_cast<long long>(m) * lda + k]) : 0.f;
@@ -221,21 +223,21 @@ gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, in
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[4], w[4];
+      float a[TM], w[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
 #pragma unroll
       for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -583,8 +585,13 @@ void layernorm(const T* x, int ldx, const float* gamma, const float* beta, T* ou
 template <typename TA, typename TW, typename TO>
 void gemm_simt(const TA* A, int lda, const TW* W, int wsk, int wsn, TO* out, int ldc, int M, int N, int K, const float* bias,
                const float* scale, const TO* res, int ldr, int gelu, cudaStream_t s) {
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  gemm_simt_kernel<TA, TW, TO><<<grid, 256, 0, s>>>(A, lda, W, wsk, wsn, out, ldc, M, N, K, bias, scale, res, ldr, gelu);
+  if (static_cast<long long>((N + 63) / 64) * ((M + 63) / 64) >= 2 * sm_count()) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_simt_kernel<TA, TW, TO, 4><<<grid, 256, 0, s>>>(A, lda, W, wsk, wsn, out, ldc, M, N, K, bias, scale, res, ldr, gelu);
+  } else {
+    dim3 grid((N + 63) / 64, (M + 15) / 16);
+    gemm_simt_kernel<TA, TW, TO, 1><<<grid, 256, 0, s>>>(A, lda, W, wsk, wsn, out, ldc, M, N, K, bias, scale, res, ldr, gelu);
+  }
   VB_LAUNCHED();
 }
 
