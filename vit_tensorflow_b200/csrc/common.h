@@ -40,7 +40,7 @@ CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2
 // out[M,N] = epilogue(A[M,K] * Wt[N,K]^T): bf16 operands (K-major), fp32 accumulation in TMEM.
 // epilogue: (+bias[n]) -> (exact-erf GELU) -> (*scale[n]) -> (+res[m,n]); out bf16.
 struct GemmBf16 {
-  CUtensorMap tmap_a, tmap_b, tmap_c;
+  CUtensorMap tmap_a, tmap_b, tmap_c, tmap_r;   // A, B (weights), output, residual
   int M = 0, N = 0, K = 0;
   int block_n = 256;
   int cta_group = 2;                    // 2: CTA pairs (cta_group::2) on 256-row tiles; 1: single-CTA 128-row tiles

@@ -36,8 +36,8 @@ constexpr int PRODUCER_WARP = 10;        // the issue arbiter favours high warp 
 constexpr int MMA_WARP = 11;             // single-instruction-stream roles above the math-heavy epilogue warps
 constexpr int NUM_EPI_THREADS = 256;
 constexpr int STAGING_BYTES = 4096;       // per-warp slab: 32 rows x 64 bf16 columns (128-byte swizzled rows)
-constexpr int NUM_STAGING = 8;            // one 4 KB slab per epilogue warp
-constexpr int CONST_BYTES = 2 * 3 * 256 * 4;  // per-column epilogue constants (bias/c2, c1, scale) of a tile, double-buffered
+constexpr int NUM_STAGING = 16;           // two 4 KB slabs per epilogue warp (residual-in / output staging, ping-pong)
+constexpr int CONST_BYTES = 0;
 
 template <int BN, int CG>
 struct Cfg {
@@ -47,7 +47,7 @@ struct Cfg {
   static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - CONST_BYTES - 256 - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 256 or 512)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STAGING * STAGING_BYTES + CONST_BYTES + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STAGING * STAGING_BYTES + CONST_BYTES + 512 /*barriers*/ + 1024 /*align*/;
 };
 
 // Exact-erf GELU (vit.py:34) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-exact for a
@@ -77,7 +77,7 @@ __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
 template <int BN, bool GELU, bool RES, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, int M, int N, int K,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* __restrict__ ln_rows,
                  float2* __restrict__ stats_out, int stats_parts, long long* __restrict__ dbg) {
@@ -94,6 +94,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * C::STAGES + 4);
+  auto res_bar = [&](int w, int p) { return bar_base + 8u * (2 * C::STAGES + 5 + w * 2 + p); };   // per epilogue warp x slab
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to aligned base
 
   const int warp = threadIdx.x >> 5;
@@ -112,6 +113,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_c);
+    if (RES) tma_prefetch_desc(&tmap_r);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -120,6 +122,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), CG * NUM_EPI_THREADS / 32);         // the leader counts both CTAs' epilogue warps
     }
+    for (int w = 0; w < NUM_EPI_THREADS / 32; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -222,12 +225,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q = e & 3;
     const int hf = e >> 2;
     const int row_local = q * 32 + lane;
-    const uint32_t slab = smem_staging + e * 4096;                 // 32 rows x 128 bytes, 1024-aligned
-    const uint32_t srow = slab + lane * 128;
-    const int etid = threadIdx.x - EPI_WARP0 * 32;                 // 0..255: one tile column per epilogue thread
+    const uint32_t slab0 = smem_staging + e * 2 * 4096;            // two slabs of 32 rows x 128 bytes, 1024-aligned
     constexpr int CHUNKS = BN / 128;                               // 64-column chunks per warp per tile
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t cnt = 0;                                              // chunks processed by this warp (slab = cnt & 1)
+    uint32_t rph = 0;                                              // bit p = mbarrier phase of slab p's residual barrier
     // folded LayerNorm of the A operand: y = rstd * acc + (-rstd * mu) * c1[n] + c2[n]   (c2 arrives through `bias`);
     // (mu, rstd) of this thread's row, prefetched one tile ahead
     float2 ln_next = make_float2(0.f, 1.f);
@@ -235,6 +238,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int r0 = (tile0 / tiles_n) * TM + cta_rank * BM + row_local;
       if (r0 < M) ln_next = ln_rows[r0];
     }
+    // Residual tiles come in through TMA (32 rows x 64 columns into the slab that will also stage the output), one
+    // chunk ahead of the math.  Per-thread row reads (32 distinct 128-byte lines per LDG) saturated the LSU: clock64
+    // traces showed ~4 K cycles per chunk in those loads, 2.4x the tile's MMA time at K = 768.
+    auto res_coords = [&](uint32_t k, int& cx, int& cy) {           // k-th chunk of this warp in schedule order
+      const int tt = tile0 + static_cast<int>(k / CHUNKS) * tile_step;
+      cx = (tt % tiles_n) * BN + (hf * CHUNKS + static_cast<int>(k % CHUNKS)) * 64;
+      cy = (tt / tiles_n) * TM + cta_rank * BM + q * 32;
+      return tt < num_tiles;
+    };
+    auto res_issue = [&](uint32_t k) {                              // lane 0 only
+      int cx, cy;
+      if (res_coords(k, cx, cy) && cx < N) {
+        mbar_arrive_expect_tx(res_bar(e, k & 1), 4096);
+        tma_load_2d(slab0 + (k & 1) * 4096, &tmap_r, res_bar(e, k & 1), cx, cy);
+      }
+    };
+    if (RES && lane == 0) res_issue(0);
     for (int t = tile0; t < num_tiles; t += tile_step) {
       const int m0 = (t / tiles_n) * TM + cta_rank * BM;
       const int n0 = (t % tiles_n) * BN;
@@ -245,93 +265,86 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int rn = ((t + tile_step) / tiles_n) * TM + cta_rank * BM + row_local;
         if (rn < M) ln_next = ln_rows[rn];
       }
-      // Stage this tile's per-column constants in shared memory (one column per thread, coalesced); the chunk loop then
-      // reads them as broadcast LDS instead of exposing a global-load round trip per 16 columns (clock64 traces showed
-      // ~1.3 K cycles per 16-column group with __ldg constants, whatever the epilogue math).
-      const uint32_t cbase = smem_consts + acc * (3 * 256 * 4);
-      {
-        const int n = n0 + etid;
-        float cb = 0.f, c1v = 0.f, sc = 1.f;
-        if (etid < BN && n < N) {
-          if (bias != nullptr) cb = __ldg(bias + n);
-          if (ln_c1 != nullptr) c1v = __ldg(ln_c1 + n);
-          if (scale != nullptr) sc = __ldg(scale + n);
-        }
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbase + etid * 4), "f"(cb) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbase + 1024 + etid * 4), "f"(c1v) : "memory");
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(cbase + 2048 + etid * 4), "f"(sc) : "memory");
-      }
-      named_bar_sync(1, NUM_EPI_THREADS);
       if (lane == 0 && q == 0) trace(1 + hf, 10);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       if (lane == 0 && q == 0) trace(1 + hf, 11);
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
+      for (int c = 0; c < CHUNKS; ++c, ++cnt) {
         const int cc = hf * CHUNKS + c;                             // 64-column chunk of the tile
         const int ncol0 = n0 + cc * 64;
         const bool col_ok = ncol0 < N;                              // N % 64 == 0: a chunk is entirely in or out
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cc * 64;
-        // residual row segment (128 bytes) and all four TMEM loads of the chunk are issued up front
-        uint4 rres[8];
-        const bool res_ok = RES && col_ok && row < M;
-        if (RES) {
-          const uint4* rp = reinterpret_cast<const uint4*>(res + (res_ok ? static_cast<size_t>(row) * ldr + ncol0 : 0));
-#pragma unroll
-          for (int k = 0; k < 8; ++k) rres[k] = res_ok ? rp[k] : make_uint4(0, 0, 0, 0);
-        }
+        const uint32_t slab = slab0 + (cnt & 1u) * 4096;
+        const uint32_t srow = slab + lane * 128;
         uint32_t v[4][16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld_32x32b_x16(tcol + g * 16, v[g]);
+        // the OTHER slab was last read by the TMA store of the previous chunk: once that has drained, prefetch the next
+        // chunk's residual into it (or simply make it writable again)
+        if (lane == 0) {
+          bulk_wait_group_read<0>();
+          if (RES) res_issue(cnt + 1);
+        }
         tmem_ld_wait();
         if (lane == 0 && q == 0) trace(1 + hf, 30 + c);
-        // the slab must have been fully read by this warp's previous TMA store
-        if (lane == 0) bulk_wait_group_read<0>();
+        if (RES && col_ok) {                                        // this chunk's residual has landed
+          mbar_wait(res_bar(e, cnt & 1u), (rph >> (cnt & 1u)) & 1u);
+          rph ^= 1u << (cnt & 1u);
+        }
         __syncwarp();
         if (lane == 0 && q == 0) trace(1 + hf, 40 + c);
         f32x2 st1 = 0ull, st2 = 0ull;                               // (sum, sum of squares) of the stored bf16 outputs
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          const uint32_t coff = cbase + (cc * 64 + g * 16) * 4;
+          const int ncol = ncol0 + g * 16;
           f32x2 f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = pack2u(v[g][2 * j], v[g][2 * j + 1]);
-          if (ln_c1 != nullptr) {
+          if (col_ok) {
+            if (ln_c1 != nullptr) {
+              const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(ln_c1 + ncol);
+              const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              f32x2 c0, c1p, b0, b1;
-              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(c0), "=l"(c1p) : "r"(coff + 1024 + k * 16));
-              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(coff + k * 16));
-              f[2 * k + 0] = fma2(f[2 * k + 0], ln_rstd2, fma2(c0, ln_nmr2, b0));
-              f[2 * k + 1] = fma2(f[2 * k + 1], ln_rstd2, fma2(c1p, ln_nmr2, b1));
+              for (int k = 0; k < 4; ++k) {
+                const ulonglong2 c4 = __ldg(cp + k), b4 = __ldg(bp + k);
+                f[2 * k + 0] = fma2(f[2 * k + 0], ln_rstd2, fma2(c4.x, ln_nmr2, b4.x));
+                f[2 * k + 1] = fma2(f[2 * k + 1], ln_rstd2, fma2(c4.y, ln_nmr2, b4.y));
+              }
+            } else if (bias != nullptr) {
+              const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const ulonglong2 b4 = __ldg(bp + k);
+                f[2 * k + 0] = add2(f[2 * k + 0], b4.x);
+                f[2 * k + 1] = add2(f[2 * k + 1], b4.y);
+              }
             }
-          } else if (bias != nullptr) {
+            if (GELU) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              f32x2 b0, b1;
-              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "r"(coff + k * 16));
-              f[2 * k + 0] = add2(f[2 * k + 0], b0);
-              f[2 * k + 1] = add2(f[2 * k + 1], b1);
+              for (int j = 0; j < 8; ++j) f[j] = gelu_erf2(f[j]);
             }
-          }
-          if (GELU) {
+            if (scale != nullptr) {
+              const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(scale + ncol);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = gelu_erf2(f[j]);
-          }
-          if (scale != nullptr) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              f32x2 s0, s1;
-              asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(s0), "=l"(s1) : "r"(coff + 2048 + k * 16));
-              f[2 * k + 0] = mul2(f[2 * k + 0], s0);
-              f[2 * k + 1] = mul2(f[2 * k + 1], s1);
+              for (int k = 0; k < 4; ++k) {
+                const ulonglong2 s4 = __ldg(sp + k);
+                f[2 * k + 0] = mul2(f[2 * k + 0], s4.x);
+                f[2 * k + 1] = mul2(f[2 * k + 1], s4.y);
+              }
             }
-          }
-          if (RES) {
-            const uint32_t w8[8] = {rres[2 * g].x, rres[2 * g].y, rres[2 * g].z, rres[2 * g].w,
-                                    rres[2 * g + 1].x, rres[2 * g + 1].y, rres[2 * g + 1].z, rres[2 * g + 1].w};
+            if (RES) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = add2(f[i], bf16x2_to_f32x2(w8[i]));
+              for (int k = 0; k < 2; ++k) {
+                const uint32_t slot = static_cast<uint32_t>((g * 2 + k) ^ (lane & 7));
+                uint32_t w0, w1, w2, w3;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3) : "r"(srow + slot * 16));
+                f[4 * k + 0] = add2(f[4 * k + 0], bf16x2_to_f32x2(w0));
+                f[4 * k + 1] = add2(f[4 * k + 1], bf16x2_to_f32x2(w1));
+                f[4 * k + 2] = add2(f[4 * k + 2], bf16x2_to_f32x2(w2));
+                f[4 * k + 3] = add2(f[4 * k + 3], bf16x2_to_f32x2(w3));
+              }
+            }
           }
           uint32_t pk[8];
 #pragma unroll
@@ -432,7 +445,7 @@ void launch(const GemmBf16& g, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
+  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.tmap_r, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
                              reinterpret_cast<const float2*>(g.ln_rows), reinterpret_cast<float2*>(g.stats_out), g.stats_parts, gemm_trace_buffer()));
   count_launch();
 }
@@ -505,6 +518,7 @@ GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt
   g.tmap_a = make_tmap_2d(A, K, M, static_cast<uint64_t>(lda) * 2, BK, BM);
   g.tmap_b = make_tmap_2d(Wt, K, N, static_cast<uint64_t>(ldw) * 2, BK, g.block_n / g.cta_group);
   g.tmap_c = make_tmap_2d(out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 32);
+  g.tmap_r = res ? make_tmap_2d(res, N, M, static_cast<uint64_t>(ldr) * 2, 64, 32) : g.tmap_c;
   const int tm = BM * g.cta_group;
   const int tiles = ((M + tm - 1) / tm) * ((N + g.block_n - 1) / g.block_n);
   const int clusters = sm_count() / g.cta_group;

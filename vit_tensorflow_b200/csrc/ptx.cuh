@@ -278,19 +278,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // ------------------------------------------------------------------------------------------ packed fp32x2 math
 // Blackwell issues two fp32 FMAs per lane per instruction (SASS FFMA2 / FMUL2 / FADD2) on 64-bit register pairs.
 typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
+// pack / unpack are plain integer expressions on the 64-bit value: ptxas maps them onto the halves of a register pair
+// (inline "mov.b64" forced real MOV instructions, ~12 per GELU pair).
 __device__ __forceinline__ f32x2 pack2u(uint32_t lo, uint32_t hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
+  return (static_cast<f32x2>(hi) << 32) | static_cast<f32x2>(lo);
 }
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { return pack2u(__float_as_uint(lo), __float_as_uint(hi)); }
 __device__ __forceinline__ f32x2 splat2(float v) { return pack2(v, v); }
 __device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  lo = __uint_as_float(static_cast<uint32_t>(v));
+  hi = __uint_as_float(static_cast<uint32_t>(v >> 32));
 }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
   f32x2 r;
