@@ -8,7 +8,9 @@
 #include "attention.cuh"
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace vb {
 namespace {
@@ -216,6 +218,216 @@ mid_fused_kernel(float* __restrict__ S, const float* __restrict__ mix_a, const f
     for (int j = threadIdx.x; j < nk; j += blockDim.x) base[h * plane + j] = buf[h * nk + j];
 }
 
+
+// ------------------------------------------------------------------------------------------ fused variant kernel
+// One block = 16 query rows of one image, ALL heads: the [heads, 16, nk] score block lives in shared memory, so the
+// cross-head steps (CaiT talking heads cait.py:123-125, DeepViT re-attention + LayerNorm over heads deepvit.py:83-84)
+// are local, and nothing of the [b,h,n,n] tensor ever reaches HBM.
+//   phase 1  for each head: K_h -> smem, S_h = scale * Q_h K_h^T by mma.sync (warps split the key tiles)
+//   phase 2  pre-mix (v2) -> softmax -> post-mix (v2) / mix + LN over heads (v1); probabilities rewritten in place as
+//            bf16 hi|lo pairs (fp32 word -> two bf16 halves) so that phase 3 can feed P at ~2^-17 precision
+//   phase 3  for each head: V_g^T -> smem, O_g = P_g V_g by mma.sync (one 8-wide d tile per warp)
+constexpr int FV_ROWS = 16;
+constexpr int FV_THREADS = 256;
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+
+template <int H>   // H = heads when known at compile time (registers instead of local arrays), 0 = run-time
+__global__ void __launch_bounds__(FV_THREADS)
+attn_variant_fused_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
+                          const __nv_bfloat16* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ out, int ldo,
+                          const float* __restrict__ mix_a, const float* __restrict__ mix_b, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, int heads, int nq, int nk, int dh, int variant, int spitch, float scale) {
+  extern __shared__ __align__(16) uint8_t fv_smem[];
+  float* Sb = reinterpret_cast<float*>(fv_smem);                                  // [heads][16][spitch]
+  const int nk16 = (nk + 15) & ~15;
+  const int kvpitch = dh + 8;                                                     // K staging: [nk][dh+8] bf16
+  const int vtpitch = nk16 + 8;                                                   // V staging: [dh][nk16+8] bf16 (transposed)
+  __nv_bfloat16* KV = reinterpret_cast<__nv_bfloat16*>(Sb + static_cast<size_t>(heads) * FV_ROWS * spitch);
+  float* Wa = reinterpret_cast<float*>(KV + max(nk16 * kvpitch, dh * vtpitch));
+  float* Wb = Wa + heads * heads;
+  const int b = blockIdx.y, i0 = blockIdx.x * FV_ROWS;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = FV_THREADS / 32;
+  const int fr = lane >> 2, fc = 2 * (lane & 3);                                  // fragment row / column pair
+
+  for (int e = threadIdx.x; e < heads * heads; e += FV_THREADS) {
+    Wa[e] = mix_a ? mix_a[e] : 0.f;
+    Wb[e] = mix_b ? mix_b[e] : 0.f;
+  }
+  // ---------------------------------------------------------------- phase 1: scores
+  const int ntiles = (nk + 7) >> 3;
+  for (int h = 0; h < heads; ++h) {
+    __syncthreads();
+    const int vec = dh >> 3;
+    for (int e = threadIdx.x; e < nk16 * vec; e += FV_THREADS) {
+      const int r = e / vec, c = (e % vec) * 8;
+      uint4 val = make_uint4(0, 0, 0, 0);
+      if (r < nk) val = *reinterpret_cast<const uint4*>(k + (static_cast<size_t>(b) * nk + r) * ldk + h * dh + c);
+      *reinterpret_cast<uint4*>(KV + r * kvpitch + c) = val;
+    }
+    __syncthreads();
+    uint32_t qa[MAXDH / 16][4];
+    {
+      const int r0 = i0 + fr, r1 = r0 + 8;
+      const __nv_bfloat16* q0 = q + (static_cast<size_t>(b) * nq + r0) * ldq + h * dh;
+      const __nv_bfloat16* q1 = q + (static_cast<size_t>(b) * nq + r1) * ldq + h * dh;
+#pragma unroll
+      for (int ks = 0; ks < MAXDH / 16; ++ks) {
+        if (ks * 16 < dh) {
+          qa[ks][0] = r0 < nq ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + fc) : 0u;
+          qa[ks][1] = r1 < nq ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + fc) : 0u;
+          qa[ks][2] = r0 < nq ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + fc + 8) : 0u;
+          qa[ks][3] = r1 < nq ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + fc + 8) : 0u;
+        }
+      }
+    }
+    float* Sh = Sb + static_cast<size_t>(h) * FV_ROWS * spitch;
+    for (int nt = warp; nt < ntiles; nt += nwarps) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < MAXDH / 16; ++ks) {
+        if (ks * 16 < dh) {
+          uint32_t bb[2];
+          const __nv_bfloat16* kr = KV + (nt * 8 + fr) * kvpitch + ks * 16 + fc;
+          bb[0] = *reinterpret_cast<const uint32_t*>(kr);
+          bb[1] = *reinterpret_cast<const uint32_t*>(kr + 8);
+          mma_bf16_16816(acc, qa[ks], bb);
+        }
+      }
+      const int c0 = nt * 8 + fc;
+      *reinterpret_cast<float2*>(Sh + fr * spitch + c0) = make_float2(acc[0] * scale, acc[1] * scale);
+      *reinterpret_cast<float2*>(Sh + (fr + 8) * spitch + c0) = make_float2(acc[2] * scale, acc[3] * scale);
+    }
+  }
+  __syncthreads();
+  // ---------------------------------------------------------------- phase 2: mix / softmax / mix (+LN)
+  auto mix = [&](const float* W, bool ln) {
+    constexpr int HM = H > 0 ? H : MIX_MAX_HEADS;
+    const int hn = H > 0 ? H : heads;
+    for (int e = threadIdx.x; e < FV_ROWS * nk; e += FV_THREADS) {
+      const int r = e / nk, j = e % nk;
+      float* col = Sb + r * spitch + j;
+      float x[HM], y[HM];
+#pragma unroll
+      for (int h = 0; h < HM; ++h) if (h < hn) x[h] = col[static_cast<size_t>(h) * FV_ROWS * spitch];
+#pragma unroll
+      for (int g = 0; g < HM; ++g) y[g] = 0.f;
+#pragma unroll
+      for (int h = 0; h < HM; ++h) {
+        if (h < hn) {
+#pragma unroll
+          for (int g = 0; g < HM; ++g) if (g < hn) y[g] = fmaf(x[h], W[h * hn + g], y[g]);
+        }
+      }
+      if (ln) {
+        float mean = 0.f;
+#pragma unroll
+        for (int g = 0; g < HM; ++g) if (g < hn) mean += y[g];
+        mean /= hn;
+        float var = 0.f;
+#pragma unroll
+        for (int g = 0; g < HM; ++g) if (g < hn) { const float d = y[g] - mean; var += d * d; }
+        const float rstd = rsqrtf(var / hn + 1e-3f);
+#pragma unroll
+        for (int g = 0; g < HM; ++g) if (g < hn) y[g] = (y[g] - mean) * rstd * gamma[g] + beta[g];
+      }
+#pragma unroll
+      for (int g = 0; g < HM; ++g) if (g < hn) col[static_cast<size_t>(g) * FV_ROWS * spitch] = y[g];
+    }
+  };
+  if (variant == 2) { mix(Wa, false); __syncthreads(); }
+  for (int row = warp; row < heads * FV_ROWS; row += nwarps) {                    // softmax, one warp per (head, query row)
+    float* r = Sb + static_cast<size_t>(row) * spitch;
+    float mx = -INFINITY;
+    for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, r[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < nk; j += 32) { const float e = __expf(r[j] - mx); r[j] = e; sum += e; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    for (int j = lane; j < nk; j += 32) r[j] *= inv;
+  }
+  __syncthreads();
+  if (variant == 1) { mix(Wa, true); __syncthreads(); }
+  if (variant == 2) { mix(Wb, false); __syncthreads(); }
+  // probabilities -> (bf16 hi | bf16 lo << 16) in place; columns >= nk of the 16-key padding become zero
+  for (int e = threadIdx.x; e < heads * FV_ROWS * nk16; e += FV_THREADS) {
+    const int j = e % nk16, row = e / nk16;
+    float* w = Sb + static_cast<size_t>(row) * spitch + j;
+    const float p = j < nk ? *w : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(p);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(p - __bfloat162float(hi));
+    *reinterpret_cast<uint32_t*>(w) = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
+  }
+  // ---------------------------------------------------------------- phase 3: O_g = P_g V_g
+  const int dtiles = dh >> 3;
+  const bool split = variant == 1;
+  for (int g = 0; g < heads; ++g) {
+    __syncthreads();
+    for (int e = threadIdx.x; e < nk16 * dh; e += FV_THREADS) {                   // V_g transposed: Vt[d][j]
+      const int j = e / dh, d = e % dh;
+      __nv_bfloat16 x = __float2bfloat16_rn(0.f);
+      if (j < nk) x = v[(static_cast<size_t>(b) * nk + j) * ldv + g * dh + d];
+      KV[d * vtpitch + j] = x;
+    }
+    __syncthreads();
+    if (warp < dtiles) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t* P0 = reinterpret_cast<const uint32_t*>(Sb + (static_cast<size_t>(g) * FV_ROWS + fr) * spitch);
+      const uint32_t* P1 = P0 + 8 * spitch;
+      for (int kk = 0; kk < nk16; kk += 16) {
+        const uint32_t w00 = P0[kk + fc], w01 = P0[kk + fc + 1], w10 = P1[kk + fc], w11 = P1[kk + fc + 1];
+        const uint32_t w02 = P0[kk + fc + 8], w03 = P0[kk + fc + 9], w12 = P1[kk + fc + 8], w13 = P1[kk + fc + 9];
+        uint32_t a[4] = {prmt(w00, w01, 0x5410), prmt(w10, w11, 0x5410), prmt(w02, w03, 0x5410), prmt(w12, w13, 0x5410)};
+        uint32_t bb[2];
+        const __nv_bfloat16* vr = KV + (warp * 8 + fr) * vtpitch + kk + fc;
+        bb[0] = *reinterpret_cast<const uint32_t*>(vr);
+        bb[1] = *reinterpret_cast<const uint32_t*>(vr + 8);
+        mma_bf16_16816(acc, a, bb);
+        if (split) {
+          uint32_t al[4] = {prmt(w00, w01, 0x7632), prmt(w10, w11, 0x7632), prmt(w02, w03, 0x7632), prmt(w12, w13, 0x7632)};
+          mma_bf16_16816(acc, al, bb);
+        }
+      }
+      const int r0 = i0 + fr, r1 = r0 + 8, c0 = g * dh + warp * 8 + fc;
+      if (r0 < nq) *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(b) * nq + r0) * ldo + c0) = __floats2bfloat162_rn(acc[0], acc[1]);
+      if (r1 < nq) *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(b) * nq + r1) * ldo + c0) = __floats2bfloat162_rn(acc[2], acc[3]);
+    }
+  }
+}
+
+// false when the score block of 16 query rows does not fit in shared memory
+bool attention_variant_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                             __nv_bfloat16* out, int ldo, int B, int nq, int nk, int heads, int dh, int variant,
+                             const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta, cudaStream_t s) {
+  const int nk16 = (nk + 15) & ~15;
+  int spitch = nk16 + 4;                                       // even, and 16 consecutive rows spread over the banks
+  if ((spitch & 31) == 0) spitch += 4;
+  const size_t kvbytes = static_cast<size_t>(std::max(nk16 * (dh + 8), dh * (nk16 + 8))) * 2;
+  const size_t smem = static_cast<size_t>(heads) * FV_ROWS * spitch * 4 + kvbytes + 2 * heads * heads * 4;
+  if (smem > 225 * 1024) return false;
+  static bool configured = false;
+  if (!configured) {
+    VB_CUDA(cudaFuncSetAttribute(attn_variant_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    VB_CUDA(cudaFuncSetAttribute(attn_variant_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    VB_CUDA(cudaFuncSetAttribute(attn_variant_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+    configured = true;
+  }
+  const float scale = 1.0f / sqrtf(static_cast<float>(dh));
+  auto kern = heads == 8 ? attn_variant_fused_kernel<8> : heads == 16 ? attn_variant_fused_kernel<16> : attn_variant_fused_kernel<0>;
+  kern<<<dim3((nq + FV_ROWS - 1) / FV_ROWS, B), FV_THREADS, smem, s>>>(
+      q, ldq, k, ldk, v, ldv, out, ldo, mix_a, mix_b, ln_gamma, ln_beta, heads, nq, nk, dh, variant, spitch, scale);
+  VB_CUDA(cudaGetLastError());
+  count_launch();
+  return true;
+}
+
 }  // namespace
 
 bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
@@ -224,6 +436,9 @@ bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16*
   if (dh % 16 != 0 || dh > MAXDH || heads > MIX_MAX_HEADS) return false;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return false;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k)) % 16) return false;
+  if (dh <= 64 && (ldo % 2) == 0 && getenv("VB_FUSED_VARIANT") != nullptr &&
+      attention_variant_fused(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, ln_gamma, ln_beta, s))
+    return true;
   const size_t smem = (static_cast<size_t>(heads) * nk + 2 * heads * heads) * sizeof(float);
   if (smem > 200 * 1024) return false;
   static bool configured = false;

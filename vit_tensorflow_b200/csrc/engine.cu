@@ -1018,16 +1018,16 @@ int vb_op_linear(int32_t precision, const float* a, const float* w, const float*
       GemmBf16 g = gemm_bf16_plan(da, K, static_cast<const __nv_bfloat16*>(dWt.p), K, dout, N, M, N, K, db, ds, dr, N, gelu != 0);
       if (const char* trace_path = getenv("VB_GEMM_TRACE")) {   // one traced launch, dumped as text: role tag clock
         DevMem dTrace;
-        dTrace.ensure(3 * 512 * 8);
-        VB_CUDA(cudaMemset(dTrace.p, 0, 3 * 512 * 8));
+        dTrace.ensure(4 * 512 * 8);
+        VB_CUDA(cudaMemset(dTrace.p, 0, 4 * 512 * 8));
         gemm_trace_buffer() = static_cast<long long*>(dTrace.p);
         gemm_bf16_run(g, 0);
         VB_CUDA(cudaDeviceSynchronize());
         gemm_trace_buffer() = nullptr;
-        std::vector<long long> h(3 * 512);
+        std::vector<long long> h(4 * 512);
         VB_CUDA(cudaMemcpy(h.data(), dTrace.p, h.size() * 8, cudaMemcpyDeviceToHost));
         if (FILE* f = fopen(trace_path, "w")) {
-          for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 4; ++r)
             for (int i = 0; i < 250 && h[r * 512 + 2 * i + 1] != 0; ++i) fprintf(f, "%d %lld %lld\n", r, h[r * 512 + 2 * i], h[r * 512 + 2 * i + 1]);
           fclose(f);
         }

@@ -7,16 +7,18 @@
 // to_out + residual (vit.py:62-69,101), MLP fc1+GELU / fc2 + residual (vit.py:38-44,102), CaiT to_q/to_kv
 // (cait.py:94-95) with LayerScale folded in (cait.py:48).
 //
-// Structure (one CTA per SM, 384 threads, static round-robin tile scheduler).  CG = 2 pairs two SMs
+// Structure (one CTA per SM, 448 threads, static round-robin tile scheduler).  CG = 2 pairs two SMs
 // (cta_group::2, a 2-CTA cluster) on one 256 x BN tile: each CTA stages its own 128 A rows and HALF of the B rows,
 // the leader CTA issues M = 256 MMAs that read B from both CTAs' shared memory.  Per SM this cuts the TMA-write +
 // UMMA-read shared-memory traffic from 192 to 128 B/clk -- the 1-CTA form measured 65 % tensor-pipe activity
 // (profiles/r01_ncu_gemm_qkv_1cta.txt), exactly the 128/192 shared-memory-bandwidth bound.
-//   warp 10     TMA producer: A tile 128x64 + B tile (BN/CG)x64 per k-block into a STAGES-deep 128B-swizzled ring
-//   warp 11     MMA issuer (leader CTA): one thread issues tcgen05.mma (128*CG x BN x 16) into a double-buffered
+//   warp 12     TMA producer: A tile 128x64 + B tile (BN/CG)x64 per k-block into a STAGES-deep 128B-swizzled ring
+//   warp 13     MMA issuer (leader CTA): one thread issues tcgen05.mma (128*CG x BN x 16) into a double-buffered
 //               TMEM accumulator (each CTA holds its 128 rows)
-//   warps 0-7   epilogue: tcgen05.ld -> bias/GELU/LayerScale/residual in registers -> bf16 -> per-warp swizzled smem
-//               slab (8 x 4 KB) -> per-warp TMA store.  Runs concurrently with the next tile's main loop.
+//   warps 0-11  epilogue: tcgen05.ld -> bias/GELU/LayerScale/residual in registers -> bf16 -> per-warp swizzled smem
+//               slab -> per-warp TMA store.  Three warps per TMEM lane quarter (two for 128-wide tiles) take the
+//               64-column chunks of the tile stream round-robin, so a warp owns 4/3 chunks per 256-wide tile and
+//               the chunk time (about 3 K cycles with GELU) stays under the 5.3 K-cycle MMA time of a K = 768 tile.
 #include "common.h"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -30,13 +32,14 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARP0 = 0;             // epilogue warps 0-7 (TMEM lane quarter = warp % 4)
-constexpr int PRODUCER_WARP = 10;        // the issue arbiter favours high warp ids: keep the two latency-critical
-constexpr int MMA_WARP = 11;             // single-instruction-stream roles above the math-heavy epilogue warps
-constexpr int NUM_EPI_THREADS = 256;
+#ifndef VB_GEMM_EW
+#define VB_GEMM_EW 2                     // epilogue warps per TMEM lane quarter for 256-wide tiles (2 or 3)
+#endif
+constexpr int MAX_EPI_WARPS = 4 * VB_GEMM_EW;   // epilogue warps (TMEM lane quarter = warp % 4, chunk lane = warp / 4)
+constexpr int PRODUCER_WARP = MAX_EPI_WARPS;    // the issue arbiter favours high warp ids: keep the two latency-critical
+constexpr int MMA_WARP = MAX_EPI_WARPS + 1;     // single-instruction-stream roles above the math-heavy epilogue warps
+constexpr int NUM_THREADS = (MAX_EPI_WARPS + 2) * 32;
 constexpr int STAGING_BYTES = 4096;       // per-warp slab: 32 rows x 64 bf16 columns (128-byte swizzled rows)
-constexpr int NUM_STAGING = 16;           // two 4 KB slabs per epilogue warp (residual-in / output staging, ping-pong)
 constexpr int CONST_BYTES = 0;
 
 template <int BN, int CG>
@@ -44,37 +47,41 @@ struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;               // each CTA of a pair stages half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - CONST_BYTES - 256 - 1024) / STAGE_BYTES;
+  static constexpr int CPT = BN / 64;                               // 64-column chunks per tile
+  static constexpr int EW = CPT >= 3 ? VB_GEMM_EW : 2;                       // epilogue warps per TMEM lane quarter (<= CPT)
+  static constexpr int EPI_WARPS = 4 * EW;
+  static constexpr int NUM_STAGING = 2 * EPI_WARPS;                 // two 4 KB slabs per epilogue warp (residual-in / output, ping-pong)
+  static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - CONST_BYTES - 512 - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 256 or 512)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STAGING * STAGING_BYTES + CONST_BYTES + 512 /*barriers*/ + 1024 /*align*/;
 };
 
-// Exact-erf GELU (vit.py:34) with erf from Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, i.e. fp32-exact for a
-// bf16 result), evaluated on fp32 PAIRS: 13 FFMA2/FMUL2 + 4 MUFU (rcp, ex2) per two elements instead of erff()'s
-// ~28 instructions per element, which made the fc1 epilogue (128 GELUs per thread per tile) slower than the MMAs.
+// Exact-erf GELU (vit.py:34), written as  gelu(x) = x/2 - |x| * (E(|x|) - 1/2),  E(a) = erfc(a/sqrt2) / 2  (for x > 0
+// this is x - x E, for x < 0 it is x E), with E evaluated as 2^q(a): q is a degree-5 polynomial (weighted minimax fit
+// of log2(erfc(a/sqrt2)/2) on a in [0, 6], constant term exactly -1; tools/gelu_error.py refits and checks it).  Its
+// leading coefficient is negative and q is monotone beyond the fit range, so no clamp is needed: for |x| > 6 the tail
+// term |x| 2^q is below 6 * 2^-29 and shrinks.  Max abs error of the GELU 5.7e-7 = 0.003 bf16 ulp of the result for
+// every finite x; gelu(+inf) = +inf and gelu(-inf) = NaN as in the reference's x * Phi(x).
+// Cost on fp32 PAIRS: 8 FFMA2/FADD2/FMUL2 + 2 LOP3 + 2 MUFU.EX2 per two elements, all on register pairs in place.
+// The epilogue is issue-bound (ubench: FFMA2 1.7, MUFU 8, FMNMX/F2FP 2 cycles per warp instruction per sub-partition;
+// ncu: 770 warp instructions per 64-column chunk with the Abramowitz-Stegun rcp + ex2 form), so the form with the
+// fewest instructions, not the fewest flops, wins.
 __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
-  const f32x2 ax = abs2(x);
-  const f32x2 z = mul2(ax, splat2(0.70710678118654752440f));
-  const f32x2 den = fma2(splat2(0.3275911f), z, splat2(1.0f));
-  float d0, d1;
-  unpack2(den, d0, d1);
-  const f32x2 t = pack2(rcp_approx(d0), rcp_approx(d1));
-  f32x2 p = fma2(splat2(-1.061405429f), t, splat2(1.453152027f));      // coefficients negated: p = -poly(t)
-  p = fma2(p, t, splat2(-1.421413741f));
-  p = fma2(p, t, splat2(0.284496736f));
-  p = fma2(p, t, splat2(-0.254829592f));
-  p = mul2(p, t);
-  const f32x2 zz = mul2(mul2(z, z), splat2(-1.4426950408889634f));
-  float e0, e1;
-  unpack2(zz, e0, e1);
-  const f32x2 e = pack2(ex2_approx(e0), ex2_approx(e1));
-  const f32x2 erf_abs = fma2(p, e, splat2(1.0f));                      // erf(|x|/sqrt2)
-  const f32x2 h = mul2(x, splat2(0.5f));
-  return fma2(abs2(h), erf_abs, h);                                    // 0.5x + 0.5|x|erf(|x|/sqrt2)
+  const f32x2 na = x | 0x8000000080000000ull;                                       // -|x|
+  f32x2 q = fma2(splat2(4.881368368e-04f), na, splat2(7.198925130e-03f));          // odd coefficients negated: q(-na)
+  q = fma2(q, na, splat2(5.214704946e-02f));
+  q = fma2(q, na, splat2(-4.595955014e-01f));
+  q = fma2(q, na, splat2(1.151000619e+00f));
+  q = fma2(q, na, splat2(-1.0f));
+  float q0, q1;
+  unpack2(q, q0, q1);
+  const f32x2 e = pack2(ex2_approx(q0), ex2_approx(q1));                           // erfc(|x|/sqrt2) / 2
+  return fma2(na, add2(e, splat2(-0.5f)), mul2(x, splat2(0.5f)));
 }
 
-template <int BN, bool GELU, bool RES, int CG>
+// EPI: 0 = no per-column addend, 1 = + bias[n], 2 = folded LayerNorm (c1 = ln_c1, c2 = bias)
+template <int BN, bool GELU, bool RES, int CG, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K,
@@ -86,7 +93,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stage0 = smem_base;
   const uint32_t smem_staging = smem_base + C::STAGES * C::STAGE_BYTES;
-  const uint32_t smem_consts = smem_staging + NUM_STAGING * STAGING_BYTES;
+  const uint32_t smem_consts = smem_staging + C::NUM_STAGING * STAGING_BYTES;
   const uint32_t bar_base = smem_consts + CONST_BYTES;
   // barrier layout (8 bytes each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -120,9 +127,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), CG * NUM_EPI_THREADS / 32);         // the leader counts both CTAs' epilogue warps
+      mbar_init(tempty_bar(s), CG * C::EPI_WARPS);         // the leader counts both CTAs' epilogue warps
     }
-    for (int w = 0; w < NUM_EPI_THREADS / 32; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
+    for (int w = 0; w < C::EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -216,62 +223,70 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < EPI_WARP0 + NUM_EPI_THREADS / 32) {
-    // ===================================================================== epilogue (8 warps)
-    // Warp (q, hf) owns accumulator rows [32q, 32q+32) (its TMEM lane quarter) and the column half hf of the tile,
-    // 64 columns (one 128-byte swizzled row) at a time, with a private 4 KB staging slab and its own TMA stores:
-    // no cross-warp barrier anywhere in the epilogue.
-    const int e = warp - EPI_WARP0;
+  } else if (warp < C::EPI_WARPS) {
+    // ===================================================================== epilogue (4 x EW warps)
+    // Warp (q, j) owns accumulator rows [32q, 32q+32) (its TMEM lane quarter) and every EW-th 64-column chunk (one
+    // 128-byte swizzled row) of this CTA's tile stream, starting at chunk j, with two private 4 KB staging slabs and its
+    // own TMA loads / stores: no cross-warp barrier anywhere in the epilogue.  EW <= chunks per tile, so every warp
+    // visits every tile and releases its accumulator buffer exactly once.
+    constexpr int CPT = C::CPT, EW = C::EW;
+    const int e = warp;
     const int q = e & 3;
-    const int hf = e >> 2;
+    const int j = e >> 2;
     const int row_local = q * 32 + lane;
     const uint32_t slab0 = smem_staging + e * 2 * 4096;            // two slabs of 32 rows x 128 bytes, 1024-aligned
-    constexpr int CHUNKS = BN / 128;                               // 64-column chunks per warp per tile
-    int acc = 0;
-    uint32_t acc_phase = 0;
+    const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
+    const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * CPT;
     uint32_t cnt = 0;                                              // chunks processed by this warp (slab = cnt & 1)
     uint32_t rph = 0;                                              // bit p = mbarrier phase of slab p's residual barrier
     // folded LayerNorm of the A operand: y = rstd * acc + (-rstd * mu) * c1[n] + c2[n]   (c2 arrives through `bias`);
     // (mu, rstd) of this thread's row, prefetched one tile ahead
     float2 ln_next = make_float2(0.f, 1.f);
-    if (ln_rows != nullptr && tile0 < num_tiles) {
+    if (EPI == 2 && tile0 < num_tiles) {
       const int r0 = (tile0 / tiles_n) * TM + cta_rank * BM + row_local;
       if (r0 < M) ln_next = ln_rows[r0];
     }
     // Residual tiles come in through TMA (32 rows x 64 columns into the slab that will also stage the output), one
     // chunk ahead of the math.  Per-thread row reads (32 distinct 128-byte lines per LDG) saturated the LSU: clock64
     // traces showed ~4 K cycles per chunk in those loads, 2.4x the tile's MMA time at K = 768.
-    auto res_coords = [&](uint32_t k, int& cx, int& cy) {           // k-th chunk of this warp in schedule order
-      const int tt = tile0 + static_cast<int>(k / CHUNKS) * tile_step;
-      cx = (tt % tiles_n) * BN + (hf * CHUNKS + static_cast<int>(k % CHUNKS)) * 64;
-      cy = (tt / tiles_n) * TM + cta_rank * BM + q * 32;
-      return tt < num_tiles;
-    };
-    auto res_issue = [&](uint32_t k) {                              // lane 0 only
-      int cx, cy;
-      if (res_coords(k, cx, cy) && cx < N) {
+    auto res_issue = [&](uint32_t k) {                              // k-th chunk of this warp in schedule order; lane 0 only
+      const uint32_t kk = static_cast<uint32_t>(j) + k * EW;
+      if (kk >= total_chunks) return;
+      const int tt = tile0 + static_cast<int>(kk / CPT) * tile_step;
+      const int cx = (tt % tiles_n) * BN + static_cast<int>(kk % CPT) * 64;
+      const int cy = (tt / tiles_n) * TM + cta_rank * BM + q * 32;
+      if (cx < N) {
         mbar_arrive_expect_tx(res_bar(e, k & 1), 4096);
         tma_load_2d(slab0 + (k & 1) * 4096, &tmap_r, res_bar(e, k & 1), cx, cy);
       }
     };
     if (RES && lane == 0) res_issue(0);
-    for (int t = tile0; t < num_tiles; t += tile_step) {
-      const int m0 = (t / tiles_n) * TM + cta_rank * BM;
-      const int n0 = (t % tiles_n) * BN;
-      const int row = m0 + row_local;
-      const f32x2 ln_rstd2 = splat2(ln_next.y);
-      const f32x2 ln_nmr2 = splat2(-ln_next.x * ln_next.y);
-      if (ln_rows != nullptr && t + tile_step < num_tiles) {
-        const int rn = ((t + tile_step) / tiles_n) * TM + cta_rank * BM + row_local;
-        if (rn < M) ln_next = ln_rows[rn];
-      }
-      if (lane == 0 && q == 0) trace(1 + hf, 10);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tcgen05_fence_after();
-      if (lane == 0 && q == 0) trace(1 + hf, 11);
+    int cur_it = -1, m0 = 0, n0 = 0, row = 0;
+    f32x2 ln_rstd2 = 0ull, ln_nmr2 = 0ull;
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c, ++cnt) {
-        const int cc = hf * CHUNKS + c;                             // 64-column chunk of the tile
+    for (uint32_t kk = static_cast<uint32_t>(j); kk < total_chunks; kk += EW, ++cnt) {
+      const int it = static_cast<int>(kk / CPT);
+      const int cc = static_cast<int>(kk % CPT);                    // 64-column chunk of the tile
+      const int acc = it & 1;
+      if (it != cur_it) {                                           // first chunk of mine in this tile
+        cur_it = it;
+        const int t = tile0 + it * tile_step;
+        m0 = (t / tiles_n) * TM + cta_rank * BM;
+        n0 = (t % tiles_n) * BN;
+        row = m0 + row_local;
+        ln_rstd2 = splat2(ln_next.y);
+        ln_nmr2 = splat2(-ln_next.x * ln_next.y);
+        if (EPI == 2 && t + tile_step < num_tiles) {
+          const int rn = ((t + tile_step) / tiles_n) * TM + cta_rank * BM + row_local;
+          if (rn < M) ln_next = ln_rows[rn];
+        }
+        if (lane == 0 && q == 0) trace(1 + j, 10);
+        mbar_wait(tfull_bar(acc), static_cast<uint32_t>(it >> 1) & 1u);
+        tcgen05_fence_after();
+        if (lane == 0 && q == 0) trace(1 + j, 11);
+      }
+      {
+        const int c = cc;
         const int ncol0 = n0 + cc * 64;
         const bool col_ok = ncol0 < N;                              // N % 64 == 0: a chunk is entirely in or out
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cc * 64;
@@ -287,13 +302,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (RES) res_issue(cnt + 1);
         }
         tmem_ld_wait();
-        if (lane == 0 && q == 0) trace(1 + hf, 30 + c);
+        if (lane == 0 && q == 0) trace(1 + j, 30 + c);
         if (RES && col_ok) {                                        // this chunk's residual has landed
           mbar_wait(res_bar(e, cnt & 1u), (rph >> (cnt & 1u)) & 1u);
           rph ^= 1u << (cnt & 1u);
         }
         __syncwarp();
-        if (lane == 0 && q == 0) trace(1 + hf, 40 + c);
+        if (lane == 0 && q == 0) trace(1 + j, 40 + c);
         f32x2 st1 = 0ull, st2 = 0ull;                               // (sum, sum of squares) of the stored bf16 outputs
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -302,7 +317,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = pack2u(v[g][2 * j], v[g][2 * j + 1]);
           if (col_ok) {
-            if (ln_c1 != nullptr) {
+            if (EPI == 2) {
               const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(ln_c1 + ncol);
               const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
 #pragma unroll
@@ -311,7 +326,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 f[2 * k + 0] = fma2(f[2 * k + 0], ln_rstd2, fma2(c4.x, ln_nmr2, b4.x));
                 f[2 * k + 1] = fma2(f[2 * k + 1], ln_rstd2, fma2(c4.y, ln_nmr2, b4.y));
               }
-            } else if (bias != nullptr) {
+            } else if (EPI == 1) {
               const ulonglong2* bp = reinterpret_cast<const ulonglong2*>(bias + ncol);
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -370,23 +385,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           unpack2(st2, b0, b1);
           stats_out[static_cast<size_t>(row) * stats_parts + (ncol0 >> 6)] = make_float2(a0 + a1, b0 + b1);
         }
-        if (lane == 0 && q == 0) trace(1 + hf, 50 + c);
+        if (lane == 0 && q == 0) trace(1 + j, 50 + c);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
           if (col_ok) tma_store_2d(&tmap_c, slab, ncol0, m0 + q * 32);
           bulk_commit_group();
         }
-        if (lane == 0 && q == 0) trace(1 + hf, 20 + c);
+        if (lane == 0 && q == 0) trace(1 + j, 20 + c);
       }
-      // all TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld above)
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (CG == 2) mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);   // the leader's MMA warp owns this barrier
-        else mbar_arrive(tempty_bar(acc));
+      if (kk + EW >= total_chunks || static_cast<int>((kk + EW) / CPT) != it) {
+        // my last chunk of this tile: all my TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld above)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);   // the leader's MMA warp owns this barrier
+          else mbar_arrive(tempty_bar(acc));
+        }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_group<0>();   // all output bytes are globally visible before exit
   }
@@ -417,15 +433,15 @@ EncodeTiledFn get_encode_fn() {
 }
 
 }  // namespace
-long long*& gemm_trace_buffer() {   // debugging aid: device trace buffer [3 roles][256 (tag, clock)]; null = off
+long long*& gemm_trace_buffer() {   // debugging aid: device trace buffer [4 roles][256 (tag, clock)]; null = off
   static long long* p = nullptr;
   return p;
 }
 namespace {
 
-template <int BN, bool GELU, bool RES, int CG>
+template <int BN, bool GELU, bool RES, int CG, int EPI>
 void launch(const GemmBf16& g, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<BN, GELU, RES, CG>;
+  auto kern = gemm_bf16_kernel<BN, GELU, RES, CG, EPI>;
   static bool configured = false;
   if (!configured) {
     VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM_BYTES));
@@ -453,8 +469,14 @@ void launch(const GemmBf16& g, cudaStream_t stream) {
 template <int BN, int CG>
 void launch_epi(const GemmBf16& g, cudaStream_t stream) {
   const bool res = g.res != nullptr;
-  if (g.gelu) { if (res) launch<BN, true, true, CG>(g, stream); else launch<BN, true, false, CG>(g, stream); }
-  else        { if (res) launch<BN, false, true, CG>(g, stream); else launch<BN, false, false, CG>(g, stream); }
+  const int epi = g.ln_c1 != nullptr ? 2 : g.bias != nullptr ? 1 : 0;
+  VB_CHECK(epi != 2 || (g.bias != nullptr && g.ln_rows != nullptr), "folded LayerNorm needs c1, c2 and the row statistics");
+#define VB_GEMM_CASE(G, R, E) if (g.gelu == G && res == R && epi == E) return launch<BN, G, R, CG, E>(g, stream)
+  VB_GEMM_CASE(false, false, 0); VB_GEMM_CASE(false, false, 1); VB_GEMM_CASE(false, false, 2);
+  VB_GEMM_CASE(true, false, 0);  VB_GEMM_CASE(true, false, 1);  VB_GEMM_CASE(true, false, 2);
+  VB_GEMM_CASE(false, true, 0);  VB_GEMM_CASE(false, true, 1);  VB_GEMM_CASE(false, true, 2);
+  VB_GEMM_CASE(true, true, 0);   VB_GEMM_CASE(true, true, 1);   VB_GEMM_CASE(true, true, 2);
+#undef VB_GEMM_CASE
 }
 
 }  // namespace
