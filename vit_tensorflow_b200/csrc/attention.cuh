@@ -18,6 +18,10 @@ bool attention_fast(const T* q, int ldq, const T* k, int ldk, const T* v, int ld
                     int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* ln_gamma,
                     const float* ln_beta, cudaStream_t s);
 
+// The talking-heads / re-attention path keeps host copies of the head-mix weights keyed by their device pointers; whoever
+// frees or rewrites such weights (vb_finalize, vb_destroy, the op-level test entry) must drop them.
+void attention_mix_cache_clear();
+
 // Tensor-core (mma.sync) + fused-middle version of attention_generic for the bf16 engine; false if the shape is not covered.
 bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                            __nv_bfloat16* out, int ldo, float* S, int B, int nq, int nk, int heads, int dh, int variant,

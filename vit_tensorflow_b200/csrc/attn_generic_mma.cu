@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <tuple>
 
 namespace vb {
 namespace {
@@ -27,7 +29,7 @@ constexpr int PITCH = MAXDH + 8;   // bf16 elements; +8 keeps the fragment loads
 // S[bh, i, j] = scale * sum_d q[b,i,h,d] k[b,j,h,d];  block: 64 x 64 tile, 4 warps x (16 rows x 64 cols)
 __global__ void __launch_bounds__(128)
 scores_mma_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk, float* __restrict__ S,
-                  int heads, int nq, int nk, int dh, float scale) {
+                  int heads, int nq, int nk, int dh, float scale, int lds) {
   __shared__ __align__(16) __nv_bfloat16 Qs[64][PITCH];
   __shared__ __align__(16) __nv_bfloat16 Ks[64][PITCH];
   const int bh = blockIdx.z, b = bh / heads, h = bh % heads;
@@ -69,7 +71,7 @@ scores_mma_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloa
     for (int half = 0; half < 2; ++half) {
       const int r = r0 + half * 8;
       if (r < nq) {
-        float* dst = S + (static_cast<size_t>(bh) * nq + r) * nk + c0;
+        float* dst = S + (static_cast<size_t>(bh) * nq + r) * lds + c0;
         if (c0 < nk) dst[0] = acc[n][2 * half] * scale;
         if (c0 + 1 < nk) dst[1] = acc[n][2 * half + 1] * scale;
       }
@@ -219,216 +221,297 @@ mid_fused_kernel(float* __restrict__ S, const float* __restrict__ mix_a, const f
 }
 
 
-// ------------------------------------------------------------------------------------------ fused variant kernel
-// One block = 16 query rows of one image, ALL heads: the [heads, 16, nk] score block lives in shared memory, so the
-// cross-head steps (CaiT talking heads cait.py:123-125, DeepViT re-attention + LayerNorm over heads deepvit.py:83-84)
-// are local, and nothing of the [b,h,n,n] tensor ever reaches HBM.
-//   phase 1  for each head: K_h -> smem, S_h = scale * Q_h K_h^T by mma.sync (warps split the key tiles)
-//   phase 2  pre-mix (v2) -> softmax -> post-mix (v2) / mix + LN over heads (v1); probabilities rewritten in place as
-//            bf16 hi|lo pairs (fp32 word -> two bf16 halves) so that phase 3 can feed P at ~2^-17 precision
-//   phase 3  for each head: V_g^T -> smem, O_g = P_g V_g by mma.sync (one 8-wide d tile per warp)
-constexpr int FV_ROWS = 16;
-constexpr int FV_THREADS = 256;
+// ------------------------------------------------------------------------------------------ row-per-warp middle + bf16 PV
+// The cross-head steps (CaiT talking heads cait.py:123-125, DeepViT re-attention + LayerNorm over heads
+// deepvit.py:83-84) need, for one (image, query row), the score rows of ALL heads.  One warp owns such a row set:
+// lane l holds keys 2l, 2l+1 (+64, +128, ...) of every head in registers (JP pairs x H heads), so the head mixes are
+// register FMAs against weights that sit in the kernel-parameter constant bank, the softmax reductions are warp
+// shuffles, and there is no shared memory and no block barrier.  Rows are read as fp32 scores and rewritten IN PLACE
+// (row pitch `lds` floats >= 16-aligned nk) as bf16 probabilities: hi plane in the first nkp bf16 of the row, and for
+// DeepViT the lo plane (p - hi) in the next nkp, so the PV product can feed them to mma.sync without conversion.
+struct MixParams {
+  float wa[256];        // [H][H] pre-softmax mix (v2) / re-attention (v1)
+  float wb[256];        // [H][H] post-softmax mix (v2)
+  float gamma[16], beta[16];
+};
 
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
-
-template <int H>   // H = heads when known at compile time (registers instead of local arrays), 0 = run-time
-__global__ void __launch_bounds__(FV_THREADS)
-attn_variant_fused_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk,
-                          const __nv_bfloat16* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ out, int ldo,
-                          const float* __restrict__ mix_a, const float* __restrict__ mix_b, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, int heads, int nq, int nk, int dh, int variant, int spitch, float scale) {
-  extern __shared__ __align__(16) uint8_t fv_smem[];
-  float* Sb = reinterpret_cast<float*>(fv_smem);                                  // [heads][16][spitch]
-  const int nk16 = (nk + 15) & ~15;
-  const int kvpitch = dh + 8;                                                     // K staging: [nk][dh+8] bf16
-  const int vtpitch = nk16 + 8;                                                   // V staging: [dh][nk16+8] bf16 (transposed)
-  __nv_bfloat16* KV = reinterpret_cast<__nv_bfloat16*>(Sb + static_cast<size_t>(heads) * FV_ROWS * spitch);
-  float* Wa = reinterpret_cast<float*>(KV + max(nk16 * kvpitch, dh * vtpitch));
-  float* Wb = Wa + heads * heads;
-  const int b = blockIdx.y, i0 = blockIdx.x * FV_ROWS;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = FV_THREADS / 32;
-  const int fr = lane >> 2, fc = 2 * (lane & 3);                                  // fragment row / column pair
-
-  for (int e = threadIdx.x; e < heads * heads; e += FV_THREADS) {
-    Wa[e] = mix_a ? mix_a[e] : 0.f;
-    Wb[e] = mix_b ? mix_b[e] : 0.f;
-  }
-  // ---------------------------------------------------------------- phase 1: scores
-  const int ntiles = (nk + 7) >> 3;
-  for (int h = 0; h < heads; ++h) {
-    __syncthreads();
-    const int vec = dh >> 3;
-    for (int e = threadIdx.x; e < nk16 * vec; e += FV_THREADS) {
-      const int r = e / vec, c = (e % vec) * 8;
-      uint4 val = make_uint4(0, 0, 0, 0);
-      if (r < nk) val = *reinterpret_cast<const uint4*>(k + (static_cast<size_t>(b) * nk + r) * ldk + h * dh + c);
-      *reinterpret_cast<uint4*>(KV + r * kvpitch + c) = val;
-    }
-    __syncthreads();
-    uint32_t qa[MAXDH / 16][4];
-    {
-      const int r0 = i0 + fr, r1 = r0 + 8;
-      const __nv_bfloat16* q0 = q + (static_cast<size_t>(b) * nq + r0) * ldq + h * dh;
-      const __nv_bfloat16* q1 = q + (static_cast<size_t>(b) * nq + r1) * ldq + h * dh;
+template <int H, int JP, int VARIANT>
+__global__ void __launch_bounds__(256)
+mid_rows_kernel(float* __restrict__ S, const __grid_constant__ MixParams P, int nq, int nk, int lds, int nkp, long long rows) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);      // (b, i)
+  if (row >= rows) return;
+  const long long b = row / nq;
+  const int i = static_cast<int>(row % nq);
+  float* base = S + (b * H * nq + i) * lds;                                               // head h at + h * nq * lds
+  const size_t plane = static_cast<size_t>(nq) * lds;
+  float x[JP][2][H];
 #pragma unroll
-      for (int ks = 0; ks < MAXDH / 16; ++ks) {
-        if (ks * 16 < dh) {
-          qa[ks][0] = r0 < nq ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + fc) : 0u;
-          qa[ks][1] = r1 < nq ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + fc) : 0u;
-          qa[ks][2] = r0 < nq ? *reinterpret_cast<const uint32_t*>(q0 + ks * 16 + fc + 8) : 0u;
-          qa[ks][3] = r1 < nq ? *reinterpret_cast<const uint32_t*>(q1 + ks * 16 + fc + 8) : 0u;
-        }
-      }
-    }
-    float* Sh = Sb + static_cast<size_t>(h) * FV_ROWS * spitch;
-    for (int nt = warp; nt < ntiles; nt += nwarps) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int jj = 0; jj < JP; ++jj) {
+    const int j0 = 2 * lane + 64 * jj;
 #pragma unroll
-      for (int ks = 0; ks < MAXDH / 16; ++ks) {
-        if (ks * 16 < dh) {
-          uint32_t bb[2];
-          const __nv_bfloat16* kr = KV + (nt * 8 + fr) * kvpitch + ks * 16 + fc;
-          bb[0] = *reinterpret_cast<const uint32_t*>(kr);
-          bb[1] = *reinterpret_cast<const uint32_t*>(kr + 8);
-          mma_bf16_16816(acc, qa[ks], bb);
-        }
-      }
-      const int c0 = nt * 8 + fc;
-      *reinterpret_cast<float2*>(Sh + fr * spitch + c0) = make_float2(acc[0] * scale, acc[1] * scale);
-      *reinterpret_cast<float2*>(Sh + (fr + 8) * spitch + c0) = make_float2(acc[2] * scale, acc[3] * scale);
+    for (int h = 0; h < H; ++h) {
+      float2 v = make_float2(0.f, 0.f);
+      if (j0 < nkp) v = *reinterpret_cast<const float2*>(base + h * plane + j0);           // columns [nk, nkp) hold garbage: masked below
+      x[jj][0][h] = v.x;
+      x[jj][1][h] = v.y;
     }
   }
-  __syncthreads();
-  // ---------------------------------------------------------------- phase 2: mix / softmax / mix (+LN)
-  auto mix = [&](const float* W, bool ln) {
-    constexpr int HM = H > 0 ? H : MIX_MAX_HEADS;
-    const int hn = H > 0 ? H : heads;
-    for (int e = threadIdx.x; e < FV_ROWS * nk; e += FV_THREADS) {
-      const int r = e / nk, j = e % nk;
-      float* col = Sb + r * spitch + j;
-      float x[HM], y[HM];
+  auto mix = [&](float (&v)[H], const float* W) {                                          // v[g] <- sum_h v[h] W[h][g]
+    float y[H];
 #pragma unroll
-      for (int h = 0; h < HM; ++h) if (h < hn) x[h] = col[static_cast<size_t>(h) * FV_ROWS * spitch];
+    for (int g = 0; g < H; ++g) y[g] = 0.f;
 #pragma unroll
-      for (int g = 0; g < HM; ++g) y[g] = 0.f;
+    for (int h = 0; h < H; ++h)
 #pragma unroll
-      for (int h = 0; h < HM; ++h) {
-        if (h < hn) {
+      for (int g = 0; g < H; ++g) y[g] = fmaf(v[h], W[h * H + g], y[g]);
 #pragma unroll
-          for (int g = 0; g < HM; ++g) if (g < hn) y[g] = fmaf(x[h], W[h * hn + g], y[g]);
-        }
-      }
-      if (ln) {
-        float mean = 0.f;
-#pragma unroll
-        for (int g = 0; g < HM; ++g) if (g < hn) mean += y[g];
-        mean /= hn;
-        float var = 0.f;
-#pragma unroll
-        for (int g = 0; g < HM; ++g) if (g < hn) { const float d = y[g] - mean; var += d * d; }
-        const float rstd = rsqrtf(var / hn + 1e-3f);
-#pragma unroll
-        for (int g = 0; g < HM; ++g) if (g < hn) y[g] = (y[g] - mean) * rstd * gamma[g] + beta[g];
-      }
-#pragma unroll
-      for (int g = 0; g < HM; ++g) if (g < hn) col[static_cast<size_t>(g) * FV_ROWS * spitch] = y[g];
-    }
+    for (int g = 0; g < H; ++g) v[g] = y[g];
   };
-  if (variant == 2) { mix(Wa, false); __syncthreads(); }
-  for (int row = warp; row < heads * FV_ROWS; row += nwarps) {                    // softmax, one warp per (head, query row)
-    float* r = Sb + static_cast<size_t>(row) * spitch;
+  if (VARIANT == 2) {
+#pragma unroll
+    for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) mix(x[jj][e], P.wa);
+  }
+  // softmax over the keys, per head
+#pragma unroll
+  for (int h = 0; h < H; ++h) {
     float mx = -INFINITY;
-    for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, r[j]);
+#pragma unroll
+    for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+        if (2 * lane + 64 * jj + e < nk) mx = fmaxf(mx, x[jj][e][h]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
-    for (int j = lane; j < nk; j += 32) { const float e = __expf(r[j] - mx); r[j] = e; sum += e; }
+#pragma unroll
+    for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const float ex = (2 * lane + 64 * jj + e < nk) ? __expf(x[jj][e][h] - mx) : 0.f;
+        x[jj][e][h] = ex;
+        sum += ex;
+      }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float inv = 1.0f / sum;
-    for (int j = lane; j < nk; j += 32) r[j] *= inv;
+#pragma unroll
+    for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) x[jj][e][h] *= inv;
   }
-  __syncthreads();
-  if (variant == 1) { mix(Wa, true); __syncthreads(); }
-  if (variant == 2) { mix(Wb, false); __syncthreads(); }
-  // probabilities -> (bf16 hi | bf16 lo << 16) in place; columns >= nk of the 16-key padding become zero
-  for (int e = threadIdx.x; e < heads * FV_ROWS * nk16; e += FV_THREADS) {
-    const int j = e % nk16, row = e / nk16;
-    float* w = Sb + static_cast<size_t>(row) * spitch + j;
-    const float p = j < nk ? *w : 0.f;
-    const __nv_bfloat16 hi = __float2bfloat16_rn(p);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(p - __bfloat162float(hi));
-    *reinterpret_cast<uint32_t*>(w) = static_cast<uint32_t>(__bfloat16_as_ushort(hi)) | (static_cast<uint32_t>(__bfloat16_as_ushort(lo)) << 16);
-  }
-  // ---------------------------------------------------------------- phase 3: O_g = P_g V_g
-  const int dtiles = dh >> 3;
-  const bool split = variant == 1;
-  for (int g = 0; g < heads; ++g) {
-    __syncthreads();
-    for (int e = threadIdx.x; e < nk16 * dh; e += FV_THREADS) {                   // V_g transposed: Vt[d][j]
-      const int j = e / dh, d = e % dh;
-      __nv_bfloat16 x = __float2bfloat16_rn(0.f);
-      if (j < nk) x = v[(static_cast<size_t>(b) * nk + j) * ldv + g * dh + d];
-      KV[d * vtpitch + j] = x;
+#pragma unroll
+  for (int jj = 0; jj < JP; ++jj)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      if (VARIANT == 2) mix(x[jj][e], P.wb);
+      if (VARIANT == 1) {
+        mix(x[jj][e], P.wa);
+        float mean = 0.f;
+#pragma unroll
+        for (int g = 0; g < H; ++g) mean += x[jj][e][g];
+        mean *= 1.0f / H;
+        float var = 0.f;
+#pragma unroll
+        for (int g = 0; g < H; ++g) { const float d = x[jj][e][g] - mean; var = fmaf(d, d, var); }
+        const float rstd = rsqrtf(var * (1.0f / H) + 1e-3f);
+#pragma unroll
+        for (int g = 0; g < H; ++g) x[jj][e][g] = fmaf((x[jj][e][g] - mean) * rstd, P.gamma[g], P.beta[g]);
+      }
     }
-    __syncthreads();
-    if (warp < dtiles) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t* P0 = reinterpret_cast<const uint32_t*>(Sb + (static_cast<size_t>(g) * FV_ROWS + fr) * spitch);
-      const uint32_t* P1 = P0 + 8 * spitch;
-      for (int kk = 0; kk < nk16; kk += 16) {
-        const uint32_t w00 = P0[kk + fc], w01 = P0[kk + fc + 1], w10 = P1[kk + fc], w11 = P1[kk + fc + 1];
-        const uint32_t w02 = P0[kk + fc + 8], w03 = P0[kk + fc + 9], w12 = P1[kk + fc + 8], w13 = P1[kk + fc + 9];
-        uint32_t a[4] = {prmt(w00, w01, 0x5410), prmt(w10, w11, 0x5410), prmt(w02, w03, 0x5410), prmt(w12, w13, 0x5410)};
-        uint32_t bb[2];
-        const __nv_bfloat16* vr = KV + (warp * 8 + fr) * vtpitch + kk + fc;
-        bb[0] = *reinterpret_cast<const uint32_t*>(vr);
-        bb[1] = *reinterpret_cast<const uint32_t*>(vr + 8);
-        mma_bf16_16816(acc, a, bb);
-        if (split) {
-          uint32_t al[4] = {prmt(w00, w01, 0x7632), prmt(w10, w11, 0x7632), prmt(w02, w03, 0x7632), prmt(w12, w13, 0x7632)};
-          mma_bf16_16816(acc, al, bb);
+  // all lanes have read everything they need from these rows: rewrite them as bf16 (hi | lo planes), zero padded to nkp
+  __syncwarp();
+#pragma unroll
+  for (int jj = 0; jj < JP; ++jj) {
+    const int j0 = 2 * lane + 64 * jj;
+    if (j0 < nkp) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        const float p0 = j0 < nk ? x[jj][0][h] : 0.f, p1 = j0 + 1 < nk ? x[jj][1][h] : 0.f;
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(p0, p1);
+        __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(base + h * plane);
+        *reinterpret_cast<__nv_bfloat162*>(prow + j0) = hi;
+        if (VARIANT == 1) {
+          const float2 hf = __bfloat1622float2(hi);
+          *reinterpret_cast<__nv_bfloat162*>(prow + nkp + j0) = __floats2bfloat162_rn(p0 - hf.x, p1 - hf.y);
         }
       }
-      const int r0 = i0 + fr, r1 = r0 + 8, c0 = g * dh + warp * 8 + fc;
-      if (r0 < nq) *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(b) * nq + r0) * ldo + c0) = __floats2bfloat162_rn(acc[0], acc[1]);
-      if (r1 < nq) *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(b) * nq + r1) * ldo + c0) = __floats2bfloat162_rn(acc[2], acc[3]);
     }
   }
 }
 
-// false when the score block of 16 query rows does not fit in shared memory
-bool attention_variant_fused(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
-                             __nv_bfloat16* out, int ldo, int B, int nq, int nk, int heads, int dh, int variant,
-                             const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta, cudaStream_t s) {
-  const int nk16 = (nk + 15) & ~15;
-  int spitch = nk16 + 4;                                       // even, and 16 consecutive rows spread over the banks
-  if ((spitch & 31) == 0) spitch += 4;
-  const size_t kvbytes = static_cast<size_t>(std::max(nk16 * (dh + 8), dh * (nk16 + 8))) * 2;
-  const size_t smem = static_cast<size_t>(heads) * FV_ROWS * spitch * 4 + kvbytes + 2 * heads * heads * 4;
-  if (smem > 225 * 1024) return false;
-  static bool configured = false;
-  if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(attn_variant_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    VB_CUDA(cudaFuncSetAttribute(attn_variant_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    VB_CUDA(cudaFuncSetAttribute(attn_variant_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
-    configured = true;
+// out[b,i,h,d] = sum_j P[bh,i,j] v[b,j,h,d] with P in the bf16 row format written by mid_rows_kernel.
+// Block: 64 query rows of one (b, h), 4 warps x 16 rows; keys in chunks of 64 through a two-stage cp.async ring;
+// A fragments by ldmatrix, B fragments by ldmatrix.trans from the row-major V tile.
+template <bool SPLIT>
+__global__ void __launch_bounds__(128)
+pv_rows_kernel(const float* __restrict__ S, int lds, int nkp, const __nv_bfloat16* __restrict__ v, int ldv, __nv_bfloat16* __restrict__ out,
+               int ldo, int heads, int nq, int nk, int dh) {
+  constexpr int PP = 64 + 8;                                        // P tile pitch (bf16)
+  constexpr int VP = MAXDH + 8;                                     // V tile pitch (bf16)
+  extern __shared__ __align__(16) uint8_t pv_smem[];
+  // per stage: P hi [64][PP], (P lo [64][PP]), V [64][VP]
+  constexpr int P_ELEMS = 64 * PP, V_ELEMS = 64 * VP;
+  constexpr int STAGE_ELEMS = (SPLIT ? 2 : 1) * P_ELEMS + V_ELEMS;
+  __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(pv_smem);
+  const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
+  const int i0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = dh >> 3, vec = dh >> 3;
+  const int nchunks = (nk + 63) / 64;
+  auto stage = [&](int c) {
+    if (c < nchunks) {
+      __nv_bfloat16* st = sm + (c & 1) * STAGE_ELEMS;
+      const int j0 = c * 64;
+      for (int e = threadIdx.x; e < 64 * 8; e += 128) {             // P: 64 rows x 8 x 16 bytes (x2 planes)
+        const int r = e >> 3, cc = (e & 7) * 8;
+        const int ri = min(i0 + r, nq - 1);                         // rows past nq: any valid row, results discarded
+        const __nv_bfloat16* prow = reinterpret_cast<const __nv_bfloat16*>(S + (static_cast<size_t>(bh) * nq + ri) * lds);
+        const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(st + r * PP + cc));
+        if (j0 + cc < nkp) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(prow + j0 + cc) : "memory");
+          if (SPLIT) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + P_ELEMS * 2), "l"(prow + nkp + j0 + cc) : "memory");
+        } else {
+          *reinterpret_cast<uint4*>(st + r * PP + cc) = make_uint4(0, 0, 0, 0);
+          if (SPLIT) *reinterpret_cast<uint4*>(st + P_ELEMS + r * PP + cc) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      __nv_bfloat16* vs = st + (SPLIT ? 2 : 1) * P_ELEMS;
+      for (int e = threadIdx.x; e < 64 * vec; e += 128) {
+        const int r = e / vec, cc = (e % vec) * 8;
+        if (j0 + r < nk) {
+          const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(vs + r * VP + cc));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(v + (static_cast<size_t>(b) * nk + j0 + r) * ldv + h * dh + cc) : "memory");
+        } else {
+          *reinterpret_cast<uint4*>(vs + r * VP + cc) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float acc[MAXDH / 8][4];
+#pragma unroll
+  for (int n = 0; n < MAXDH / 8; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+  stage(0);
+  for (int c = 0; c < nchunks; ++c) {
+    stage(c + 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const __nv_bfloat16* st = sm + (c & 1) * STAGE_ELEMS;
+    const __nv_bfloat16* vs = st + (SPLIT ? 2 : 1) * P_ELEMS;
+    const uint32_t pa = static_cast<uint32_t>(__cvta_generic_to_shared(st + (warp * 16 + (lane & 15)) * PP + 8 * (lane >> 4)));
+    const uint32_t va = static_cast<uint32_t>(__cvta_generic_to_shared(vs + (lane & 15) * VP));
+#pragma unroll
+    for (int kk = 0; kk < 64; kk += 16) {
+      uint32_t a[4], al[4] = {0, 0, 0, 0};
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(pa + kk * 2));
+      if (SPLIT)
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(al[0]), "=r"(al[1]), "=r"(al[2]), "=r"(al[3]) : "r"(pa + P_ELEMS * 2 + kk * 2));
+#pragma unroll
+      for (int n = 0; n < MAXDH / 8; ++n) {
+        if (n < ntiles) {
+          uint32_t bb[2];
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                       : "=r"(bb[0]), "=r"(bb[1]) : "r"(va + (kk * VP + n * 8) * 2));
+          mma_bf16_16816(acc[n], a, bb);
+          if (SPLIT) mma_bf16_16816(acc[n], al, bb);
+        }
+      }
+    }
+    __syncthreads();                       // the next iteration's prefetch overwrites the other stage only after this
+  }
+  const int ar = warp * 16 + (lane >> 2), ac = 2 * (lane & 3);
+#pragma unroll
+  for (int n = 0; n < MAXDH / 8; ++n) {
+    if (n < ntiles) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int r = i0 + ar + half * 8;
+        if (r < nq)
+          *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(b) * nq + r) * ldo + h * dh + n * 8 + ac) =
+              __floats2bfloat162_rn(acc[n][2 * half], acc[n][2 * half + 1]);
+      }
+    }
+  }
+}
+
+struct MixKey {
+  const float *a, *b, *g, *be;
+  bool operator<(const MixKey& o) const { return std::tie(a, b, g, be) < std::tie(o.a, o.b, o.g, o.be); }
+};
+std::map<MixKey, MixParams>& mix_cache() {
+  static std::map<MixKey, MixParams> c;
+  return c;
+}
+
+template <int H, int JP>
+void launch_mid_rows(float* S, const MixParams& P, int nq, int nk, int lds, int nkp, long long rows, int variant, cudaStream_t s) {
+  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
+  if (variant == 1) mid_rows_kernel<H, JP, 1><<<blocks, 256, 0, s>>>(S, P, nq, nk, lds, nkp, rows);
+  else mid_rows_kernel<H, JP, 2><<<blocks, 256, 0, s>>>(S, P, nq, nk, lds, nkp, rows);
+}
+
+// Talking-heads / re-attention path for heads in {8, 16} and nk <= 256 (every BASELINE config); false otherwise.
+// The mix weights are tiny and constant per layer: they are read back once per (pointer set) and then travel as
+// kernel parameters.  S must hold B * heads * nq * round_up(nk, 16) floats.
+bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                         __nv_bfloat16* out, int ldo, float* S, int B, int nq, int nk, int heads, int dh, int variant,
+                         const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta, cudaStream_t s) {
+  if (variant != 1 && variant != 2) return false;
+  if ((heads != 8 && heads != 16) || nk > 256 || dh > MAXDH) return false;
+  if (reinterpret_cast<uintptr_t>(v) % 16 != 0 || reinterpret_cast<uintptr_t>(S) % 16 != 0) return false;
+  const int nkp = (nk + 15) & ~15;
+  const int lds = nkp;
+  auto& cache = mix_cache();                                     // weights are immutable between attention_mix_cache_clear() calls
+  const MixKey key{mix_a, mix_b, ln_gamma, ln_beta};
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    MixParams P = {};
+    const size_t hh = static_cast<size_t>(heads) * heads * sizeof(float);
+    VB_CUDA(cudaStreamSynchronize(s));
+    if (mix_a) VB_CUDA(cudaMemcpy(P.wa, mix_a, hh, cudaMemcpyDeviceToHost));
+    if (mix_b) VB_CUDA(cudaMemcpy(P.wb, mix_b, hh, cudaMemcpyDeviceToHost));
+    if (ln_gamma) VB_CUDA(cudaMemcpy(P.gamma, ln_gamma, heads * sizeof(float), cudaMemcpyDeviceToHost));
+    if (ln_beta) VB_CUDA(cudaMemcpy(P.beta, ln_beta, heads * sizeof(float), cudaMemcpyDeviceToHost));
+    it = cache.emplace(key, P).first;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  auto kern = heads == 8 ? attn_variant_fused_kernel<8> : heads == 16 ? attn_variant_fused_kernel<16> : attn_variant_fused_kernel<0>;
-  kern<<<dim3((nq + FV_ROWS - 1) / FV_ROWS, B), FV_THREADS, smem, s>>>(
-      q, ldq, k, ldk, v, ldv, out, ldo, mix_a, mix_b, ln_gamma, ln_beta, heads, nq, nk, dh, variant, spitch, scale);
+  scores_mma_kernel<<<dim3((nk + 63) / 64, (nq + 63) / 64, B * heads), 128, 0, s>>>(q, ldq, k, ldk, S, heads, nq, nk, dh, scale, lds);
   VB_CUDA(cudaGetLastError());
-  count_launch();
+  const long long rows = static_cast<long long>(B) * nq;
+  const int jp = (nkp + 63) / 64;
+  if (heads == 8) {
+    if (jp <= 2) launch_mid_rows<8, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    else launch_mid_rows<8, 4>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+  } else {
+    if (jp <= 2) launch_mid_rows<16, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    else launch_mid_rows<16, 4>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+  }
+  VB_CUDA(cudaGetLastError());
+  const dim3 grid((nq + 63) / 64, B * heads);
+  if (variant == 1) {
+    constexpr int smem = 2 * (2 * 64 * 72 + 64 * (MAXDH + 8)) * 2;
+    static bool configured = false;
+    if (!configured) { VB_CUDA(cudaFuncSetAttribute(pv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    pv_rows_kernel<true><<<grid, 128, smem, s>>>(S, lds, nkp, v, ldv, out, ldo, heads, nq, nk, dh);
+  } else {
+    constexpr int smem = 2 * (64 * 72 + 64 * (MAXDH + 8)) * 2;
+    static bool configured = false;
+    if (!configured) { VB_CUDA(cudaFuncSetAttribute(pv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    pv_rows_kernel<false><<<grid, 128, smem, s>>>(S, lds, nkp, v, ldv, out, ldo, heads, nq, nk, dh);
+  }
+  VB_CUDA(cudaGetLastError());
+  count_launch(3);
   return true;
 }
 
 }  // namespace
+
+void attention_mix_cache_clear() { mix_cache().clear(); }
 
 bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                            __nv_bfloat16* out, int ldo, float* S, int B, int nq, int nk, int heads, int dh, int variant,
@@ -436,9 +519,7 @@ bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16*
   if (dh % 16 != 0 || dh > MAXDH || heads > MIX_MAX_HEADS) return false;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 2)) return false;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k)) % 16) return false;
-  if (dh <= 64 && (ldo % 2) == 0 && getenv("VB_FUSED_VARIANT") != nullptr &&
-      attention_variant_fused(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, ln_gamma, ln_beta, s))
-    return true;
+  if (attention_rows_path(q, ldq, k, ldk, v, ldv, out, ldo, S, B, nq, nk, heads, dh, variant, mix_a, mix_b, ln_gamma, ln_beta, s)) return true;
   const size_t smem = (static_cast<size_t>(heads) * nk + 2 * heads * heads) * sizeof(float);
   if (smem > 200 * 1024) return false;
   static bool configured = false;
@@ -447,7 +528,7 @@ bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16*
     configured = true;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  scores_mma_kernel<<<dim3((nk + 63) / 64, (nq + 63) / 64, B * heads), 128, 0, s>>>(q, ldq, k, ldk, S, heads, nq, nk, dh, scale);
+  scores_mma_kernel<<<dim3((nk + 63) / 64, (nq + 63) / 64, B * heads), 128, 0, s>>>(q, ldq, k, ldk, S, heads, nq, nk, dh, scale, nk);
   VB_CUDA(cudaGetLastError());
   mid_fused_kernel<<<dim3(nq, B), 256, smem, s>>>(S, mix_a, mix_b, ln_gamma, ln_beta, heads, nq, nk, variant);
   VB_CUDA(cudaGetLastError());

@@ -719,7 +719,7 @@ void vb_handle::attention_dispatch(const T* q, int ldq, const T* k, int ldk, con
   ProfScope ps(this, PROF_ATTN, 4.0 * B * heads * nq * nk * dh + (variant == 1 ? 2.0 : variant == 2 ? 4.0 : 0.0) * B * nq * nk * heads * heads,
                static_cast<double>(sizeof(T)) * B * heads * dh * (2.0 * nq + 2.0 * nk), s);
   if (attention_fast<T>(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s)) return;
-  float* S = arena.get<float>(static_cast<size_t>(B) * heads * nq * nk);
+  float* S = arena.get<float>(static_cast<size_t>(B) * heads * nq * ((nk + 15) & ~15));   // row pitch padded for the bf16-P path
   attention_generic<T>(q, ldq, k, ldk, v, ldv, out, ldo, S, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s);
 }
 
@@ -889,6 +889,7 @@ int vb_set_weight(vb_handle* h, const char* name, const float* host_data, const 
 int vb_finalize(vb_handle* h) {
   return guarded(h, [&] {
     VB_CHECK(h != nullptr, "null handle");
+    attention_mix_cache_clear();
     h->finalize();
   });
 }
@@ -984,6 +985,7 @@ const char* vb_last_error(vb_handle* h) { return h ? h->error.c_str() : g_last_e
 void vb_destroy(vb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  attention_mix_cache_clear();
   for (auto& w : h->weights) if (w.dev) cudaFree(w.dev);
   h->prof_collect();
   for (auto e : h->event_pool) cudaEventDestroy(e);
@@ -1045,6 +1047,7 @@ int vb_op_attention(int32_t precision, int32_t variant, const float* q, const fl
     require_gpu();
     VB_CHECK(q && k && v && out && B > 0 && nq > 0 && nk > 0 && heads > 0 && dim_head > 0, "vb_op_attention: bad arguments");
     VB_CHECK(variant >= 0 && variant <= 2, "vb_op_attention: variant must be 0, 1 or 2");
+    attention_mix_cache_clear();
     const int inner = heads * dim_head;
     DevMem dQ, dK, dV, dO, dS, dMa, dMb, dG, dBt;
     const float* ma = mix_a ? upload<float>(dMa, mix_a, heads * heads) : nullptr;
@@ -1059,7 +1062,7 @@ int vb_op_attention(int32_t precision, int32_t variant, const float* q, const fl
       const T* v_d = upload<T>(dV, v, ck);
       dO.ensure(cq * sizeof(T));
       T* o_d = static_cast<T*>(dO.p);
-      dS.ensure(static_cast<size_t>(B) * heads * nq * nk * 4);
+      dS.ensure(static_cast<size_t>(B) * heads * nq * ((nk + 15) & ~15) * 4);
       DevMem dTrace;
       const char* trace_path = getenv("VB_ATTN_TRACE");
       if (trace_path) { dTrace.ensure(4 * 512 * 8); VB_CUDA(cudaMemset(dTrace.p, 0, 4 * 512 * 8)); attn_trace_buffer() = static_cast<long long*>(dTrace.p); }
