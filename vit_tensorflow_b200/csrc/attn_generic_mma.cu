@@ -7,6 +7,7 @@
 // Fusing these variants into the tcgen05 kernel (head mixing as in-kernel epilogues) is the next step.
 #include "attention.cuh"
 #include "kernels.cuh"
+#include "ptx.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -221,10 +222,74 @@ mid_fused_kernel(float* __restrict__ S, const float* __restrict__ mix_a, const f
 }
 
 
+// Scores for the row path: one block per (64-query-row stripe, b, h).  The stripe's Q rows and ALL keys of the head go to
+// shared memory once (cp.async), then each warp sweeps its 16 rows over the keys 8 at a time: ldmatrix fragments,
+// dh/16 MMAs and two 8-byte stores per step.  Against the 64x64-tile kernel above this loads Q once instead of once
+// per key tile and has one load/barrier phase per 64 x nk outputs instead of per 64 x 64.
+__global__ void __launch_bounds__(128)
+scores_stripe_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat16* __restrict__ k, int ldk, float* __restrict__ S,
+                     int heads, int nq, int nk, int dh, float scale, int lds) {
+  extern __shared__ __align__(16) uint8_t sc_smem[];
+  const int pitch = dh + 8;                                         // bf16; rows stay 16-byte aligned and conflict free
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(sc_smem);    // [64][pitch]
+  __nv_bfloat16* Ks = Qs + 64 * pitch;                              // [nk8][pitch]
+  const int bh = blockIdx.y, b = bh / heads, h = bh % heads;
+  const int i0 = blockIdx.x * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vec = dh >> 3, nk8 = (nk + 7) & ~7;
+  // (per-row 1-D bulk/TMA copies were tried here and in the PV kernel: 96-832 byte copies issued by one warp were
+  //  1.5-1.8x slower than these per-thread 16-byte cp.async requests)
+  for (int e = threadIdx.x; e < 64 * vec; e += 128) {
+    const int r = e / vec, c = (e % vec) * 8;
+    const int ri = min(i0 + r, nq - 1);                             // rows past nq: any valid row, never stored
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(Qs + r * pitch + c));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(q + (static_cast<size_t>(b) * nq + ri) * ldq + h * dh + c) : "memory");
+  }
+  for (int e = threadIdx.x; e < nk8 * vec; e += 128) {
+    const int r = e / vec, c = (e % vec) * 8;
+    const int rj = min(r, nk - 1);
+    const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(Ks + r * pitch + c));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(k + (static_cast<size_t>(b) * nk + rj) * ldk + h * dh + c) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  uint32_t a[MAXDH / 16][4];
+  const uint32_t qa = static_cast<uint32_t>(__cvta_generic_to_shared(Qs + (warp * 16 + (lane & 15)) * pitch + 8 * (lane >> 4)));
+#pragma unroll
+  for (int ks = 0; ks < MAXDH / 16; ++ks)
+    if (ks * 16 < dh)
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(a[ks][0]), "=r"(a[ks][1]), "=r"(a[ks][2]), "=r"(a[ks][3]) : "r"(qa + ks * 32));
+  // B fragments of one 8-key tile, two 16-wide k steps per ldmatrix.x4: lanes 0-7 / 8-15 / 16-23 / 24-31 address the
+  // tile's key rows at d offsets 0 / 8 / 16 / 24
+  const uint32_t ka = static_cast<uint32_t>(__cvta_generic_to_shared(Ks + (lane & 7) * pitch + 8 * (lane >> 3)));
+  const int fr = lane >> 2, fc = 2 * (lane & 3);
+  const int r0 = i0 + warp * 16 + fr, r1 = r0 + 8;
+  float* s0 = S + (static_cast<size_t>(bh) * nq + r0) * lds;
+  float* s1 = S + (static_cast<size_t>(bh) * nq + r1) * lds;
+  for (int nt = 0; nt < nk8 / 8; ++nt) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kp = 0; kp < MAXDH / 32; ++kp) {
+      if (kp * 32 < dh) {
+        uint32_t b0[2], b1[2];
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(b0[0]), "=r"(b0[1]), "=r"(b1[0]), "=r"(b1[1]) : "r"(ka + (nt * 8 * pitch + kp * 32) * 2));
+        mma_bf16_16816(acc, a[2 * kp], b0);
+        if (kp * 32 + 16 < dh) mma_bf16_16816(acc, a[2 * kp + 1], b1);
+      }
+    }
+    const int c0 = nt * 8 + fc;                                     // c0 even, lds even: 8-byte aligned; columns < nkp exist
+    if (r0 < nq) *reinterpret_cast<float2*>(s0 + c0) = make_float2(acc[0] * scale, acc[1] * scale);
+    if (r1 < nq) *reinterpret_cast<float2*>(s1 + c0) = make_float2(acc[2] * scale, acc[3] * scale);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ row-per-warp middle + bf16 PV
 // The cross-head steps (CaiT talking heads cait.py:123-125, DeepViT re-attention + LayerNorm over heads
 // deepvit.py:83-84) need, for one (image, query row), the score rows of ALL heads.  One warp owns such a row set:
-// lane l holds keys 2l, 2l+1 (+64, +128, ...) of every head in registers (JP pairs x H heads), so the head mixes are
+// lane l holds keys l, l+32, l+64, ... of every head in registers (JS slots x H heads), so the head mixes are
 // register FMAs against weights that sit in the kernel-parameter constant bank, the softmax reductions are warp
 // shuffles, and there is no shared memory and no block barrier.  Rows are read as fp32 scores and rewritten IN PLACE
 // (row pitch `lds` floats >= 16-aligned nk) as bf16 probabilities: hi plane in the first nkp bf16 of the row, and for
@@ -235,27 +300,40 @@ struct MixParams {
   float gamma[16], beta[16];
 };
 
-template <int H, int JP, int VARIANT>
+template <int H>
+__device__ __forceinline__ float tree_sum(const float (&v)[H]) {           // pairwise: depth log2(H) instead of H
+  float t[H];
+#pragma unroll
+  for (int g = 0; g < H; ++g) t[g] = v[g];
+#pragma unroll
+  for (int w = H / 2; w > 0; w >>= 1)
+#pragma unroll
+    for (int g = 0; g < w; ++g) t[g] += t[g + w];
+  return t[0];
+}
+
+// WPR = warps per row: with 16 heads one warp would need 7 x 16 score registers (255 registers, 8 warps per SM), so two
+// warps split the key slots (slot ts = WPR * t + w) and exchange their per-head (max, sum) once through shared memory.
+template <int H, int JS, int VARIANT, int WPR>
 __global__ void __launch_bounds__(256)
 mid_rows_kernel(float* __restrict__ S, const __grid_constant__ MixParams P, int nq, int nk, int lds, int nkp, long long rows) {
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);      // (b, i)
-  if (row >= rows) return;
+  constexpr int RPB = 8 / WPR;                                                            // rows per block
+  __shared__ float2 stat[WPR > 1 ? RPB : 1][WPR][H];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = warp % WPR, rl = warp / WPR;
+  const long long row_raw = static_cast<long long>(blockIdx.x) * RPB + rl;                // (b, i)
+  const bool live = row_raw < rows;
+  const long long row = live ? row_raw : rows - 1;                                        // dead warps shadow a valid row, no stores
   const long long b = row / nq;
   const int i = static_cast<int>(row % nq);
   float* base = S + (b * H * nq + i) * lds;                                               // head h at + h * nq * lds
   const size_t plane = static_cast<size_t>(nq) * lds;
-  float x[JP][2][H];
+  float x[JS][H];                                                                         // key lane + 32 (WPR t + w) of every head
 #pragma unroll
-  for (int jj = 0; jj < JP; ++jj) {
-    const int j0 = 2 * lane + 64 * jj;
+  for (int t = 0; t < JS; ++t) {
+    const int j = lane + 32 * (WPR * t + w);
 #pragma unroll
-    for (int h = 0; h < H; ++h) {
-      float2 v = make_float2(0.f, 0.f);
-      if (j0 < nkp) v = *reinterpret_cast<const float2*>(base + h * plane + j0);           // columns [nk, nkp) hold garbage: masked below
-      x[jj][0][h] = v.x;
-      x[jj][1][h] = v.y;
-    }
+    for (int h = 0; h < H; ++h) x[t][h] = j < nk ? base[h * plane + j] : 0.f;
   }
   auto mix = [&](float (&v)[H], const float* W) {                                          // v[g] <- sum_h v[h] W[h][g]
     float y[H];
@@ -270,73 +348,77 @@ mid_rows_kernel(float* __restrict__ S, const __grid_constant__ MixParams P, int 
   };
   if (VARIANT == 2) {
 #pragma unroll
-    for (int jj = 0; jj < JP; ++jj)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) mix(x[jj][e], P.wa);
+    for (int t = 0; t < JS; ++t) mix(x[t], P.wa);
   }
-  // softmax over the keys, per head
+  // softmax over the keys, per head: this warp's (max, sum of exp relative to it), merged across the row's warps
+  float fac[H];
 #pragma unroll
   for (int h = 0; h < H; ++h) {
     float mx = -INFINITY;
 #pragma unroll
-    for (int jj = 0; jj < JP; ++jj)
-#pragma unroll
-      for (int e = 0; e < 2; ++e)
-        if (2 * lane + 64 * jj + e < nk) mx = fmaxf(mx, x[jj][e][h]);
+    for (int t = 0; t < JS; ++t)
+      if (lane + 32 * (WPR * t + w) < nk) mx = fmaxf(mx, x[t][h]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
 #pragma unroll
-    for (int jj = 0; jj < JP; ++jj)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const float ex = (2 * lane + 64 * jj + e < nk) ? __expf(x[jj][e][h] - mx) : 0.f;
-        x[jj][e][h] = ex;
-        sum += ex;
-      }
+    for (int t = 0; t < JS; ++t) {
+      const float ex = (lane + 32 * (WPR * t + w) < nk) ? __expf(x[t][h] - mx) : 0.f;     // a warp without valid keys: mx = -inf, all 0
+      x[t][h] = ex;
+      sum += ex;
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
+    if (WPR == 1) fac[h] = 1.0f / sum;
+    else {
+      if (lane == 0) stat[rl][w][h] = make_float2(mx, sum);
+      fac[h] = mx;
+    }
+  }
+  if (WPR > 1) {
+    __syncthreads();
 #pragma unroll
-    for (int jj = 0; jj < JP; ++jj)
+    for (int h = 0; h < H; ++h) {
+      float m = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) x[jj][e][h] *= inv;
+      for (int u = 0; u < WPR; ++u) m = fmaxf(m, stat[rl][u][h].x);
+      float l = 0.f;
+#pragma unroll
+      for (int u = 0; u < WPR; ++u) l += stat[rl][u][h].y * __expf(stat[rl][u][h].x - m);
+      fac[h] = __expf(fac[h] - m) / l;                                                     // exp(x - m_w) * fac = exp(x - m) / l
+    }
   }
 #pragma unroll
-  for (int jj = 0; jj < JP; ++jj)
+  for (int t = 0; t < JS; ++t) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      if (VARIANT == 2) mix(x[jj][e], P.wb);
-      if (VARIANT == 1) {
-        mix(x[jj][e], P.wa);
-        float mean = 0.f;
+    for (int h = 0; h < H; ++h) x[t][h] *= fac[h];
+    if (VARIANT == 2) mix(x[t], P.wb);
+    if (VARIANT == 1) {
+      mix(x[t], P.wa);
+      const float mean = tree_sum<H>(x[t]) * (1.0f / H);
+      float d2[H];
 #pragma unroll
-        for (int g = 0; g < H; ++g) mean += x[jj][e][g];
-        mean *= 1.0f / H;
-        float var = 0.f;
+      for (int g = 0; g < H; ++g) { x[t][g] -= mean; d2[g] = x[t][g] * x[t][g]; }
+      const float rstd = rsqrtf(tree_sum<H>(d2) * (1.0f / H) + 1e-3f);
 #pragma unroll
-        for (int g = 0; g < H; ++g) { const float d = x[jj][e][g] - mean; var = fmaf(d, d, var); }
-        const float rstd = rsqrtf(var * (1.0f / H) + 1e-3f);
-#pragma unroll
-        for (int g = 0; g < H; ++g) x[jj][e][g] = fmaf((x[jj][e][g] - mean) * rstd, P.gamma[g], P.beta[g]);
-      }
+      for (int g = 0; g < H; ++g) x[t][g] = fmaf(x[t][g] * rstd, P.gamma[g], P.beta[g]);
     }
-  // all lanes have read everything they need from these rows: rewrite them as bf16 (hi | lo planes), zero padded to nkp
-  __syncwarp();
+  }
+  // every warp of the row has read everything it needs from these rows (block barrier above, or the single warp's own
+  // program order): rewrite them as bf16 (hi | lo planes), zero padded to nkp
+  if (WPR > 1) __syncthreads(); else __syncwarp();
+  if (!live) return;
 #pragma unroll
-  for (int jj = 0; jj < JP; ++jj) {
-    const int j0 = 2 * lane + 64 * jj;
-    if (j0 < nkp) {
+  for (int t = 0; t < JS; ++t) {
+    const int j = lane + 32 * (WPR * t + w);
+    if (j < nkp) {
 #pragma unroll
       for (int h = 0; h < H; ++h) {
-        const float p0 = j0 < nk ? x[jj][0][h] : 0.f, p1 = j0 + 1 < nk ? x[jj][1][h] : 0.f;
-        const __nv_bfloat162 hi = __floats2bfloat162_rn(p0, p1);
+        const float p = j < nk ? x[t][h] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(p);
         __nv_bfloat16* prow = reinterpret_cast<__nv_bfloat16*>(base + h * plane);
-        *reinterpret_cast<__nv_bfloat162*>(prow + j0) = hi;
-        if (VARIANT == 1) {
-          const float2 hf = __bfloat1622float2(hi);
-          *reinterpret_cast<__nv_bfloat162*>(prow + nkp + j0) = __floats2bfloat162_rn(p0 - hf.x, p1 - hf.y);
-        }
+        prow[j] = hi;
+        if (VARIANT == 1) prow[nkp + j] = __float2bfloat16_rn(p - __bfloat162float(hi));
       }
     }
   }
@@ -448,11 +530,12 @@ std::map<MixKey, MixParams>& mix_cache() {
   return c;
 }
 
-template <int H, int JP>
+template <int H, int JS, int WPR>
 void launch_mid_rows(float* S, const MixParams& P, int nq, int nk, int lds, int nkp, long long rows, int variant, cudaStream_t s) {
-  const unsigned blocks = static_cast<unsigned>((rows + 7) / 8);
-  if (variant == 1) mid_rows_kernel<H, JP, 1><<<blocks, 256, 0, s>>>(S, P, nq, nk, lds, nkp, rows);
-  else mid_rows_kernel<H, JP, 2><<<blocks, 256, 0, s>>>(S, P, nq, nk, lds, nkp, rows);
+  constexpr int RPB = 8 / WPR;
+  const unsigned blocks = static_cast<unsigned>((rows + RPB - 1) / RPB);
+  if (variant == 1) mid_rows_kernel<H, JS, 1, WPR><<<blocks, 256, 0, s>>>(S, P, nq, nk, lds, nkp, rows);
+  else mid_rows_kernel<H, JS, 2, WPR><<<blocks, 256, 0, s>>>(S, P, nq, nk, lds, nkp, rows);
 }
 
 // Talking-heads / re-attention path for heads in {8, 16} and nk <= 256 (every BASELINE config); false otherwise.
@@ -480,16 +563,25 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
     it = cache.emplace(key, P).first;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
-  scores_mma_kernel<<<dim3((nk + 63) / 64, (nq + 63) / 64, B * heads), 128, 0, s>>>(q, ldq, k, ldk, S, heads, nq, nk, dh, scale, lds);
+  {
+    const int sc_smem = (64 + ((nk + 7) & ~7)) * (dh + 8) * 2 + 32;   // +32: the last ldmatrix.x4 of a dh = 48 row touches its pad
+    static int configured = 0;
+    if (sc_smem > configured) {
+      VB_CUDA(cudaFuncSetAttribute(scores_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc_smem));
+      configured = sc_smem;
+    }
+    scores_stripe_kernel<<<dim3((nq + 63) / 64, B * heads), 128, sc_smem, s>>>(q, ldq, k, ldk, S, heads, nq, nk, dh, scale, lds);
+  }
   VB_CUDA(cudaGetLastError());
   const long long rows = static_cast<long long>(B) * nq;
-  const int jp = (nkp + 63) / 64;
+  const int js = (nkp + 31) / 32;                                // key slots of 32 per row: 7 for n = 196 / 197
   if (heads == 8) {
-    if (jp <= 2) launch_mid_rows<8, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
-    else launch_mid_rows<8, 4>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    if (js <= 4) launch_mid_rows<8, 4, 1>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    else if (js <= 7) launch_mid_rows<8, 7, 1>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    else launch_mid_rows<8, 8, 1>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
   } else {
-    if (jp <= 2) launch_mid_rows<16, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
-    else launch_mid_rows<16, 4>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    if (js <= 4) launch_mid_rows<16, 2, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    else launch_mid_rows<16, 4, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
   }
   VB_CUDA(cudaGetLastError());
   const dim3 grid((nq + 63) / 64, B * heads);
