@@ -394,7 +394,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __syncwarp();
       if (wq == 0 && lane == 0) trace(1 + t, 70);
     }
-    if (lane == 0) bulk_wait_group<0>();      // output bytes globally visible before exit
+    if (lane == 0) bulk_wait_group_read<0>();   // the slab must outlive the store's reads; the writes drain before the grid completes
   }
 done:
   tcgen05_fence_before();

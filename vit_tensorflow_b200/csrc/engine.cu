@@ -311,6 +311,35 @@ struct vb_handle {
     }
     return L;
   }
+  // Two bias-free Dense layers applied to the same input (CaiT to_q / to_kv on x, cait.py:114-119) as ONE tcgen05 GEMM:
+  // the packed K-major weights and the LayerNorm-fold constants of `a` and `b` are laid out back to back, so the output
+  // columns are [a | b] = [q | k | v], the layout the fused to_qkv of vit.py produces.  bf16 engine only.
+  Linear make_linear_pair(const std::string& na, int NA, const std::string& nb, int NB, int K, const Norm* fold) {
+    Linear L;
+    L.W = nullptr; L.bias = nullptr;
+    L.K = K; L.N = NA + NB; L.ldw = round_up(K, 8);
+    owned.emplace_back(new DevMem());
+    owned.back()->ensure(static_cast<size_t>(L.N) * L.ldw * sizeof(__nv_bfloat16));
+    L.Wt = static_cast<__nv_bfloat16*>(owned.back()->p);
+    float* c = nullptr;
+    if (fold) {
+      owned.emplace_back(new DevMem());
+      owned.back()->ensure(static_cast<size_t>(L.N) * 2 * sizeof(float));
+      c = static_cast<float*>(owned.back()->p);
+      L.ln_c1 = c; L.ln_c2 = c + L.N;
+    }
+    const std::string names[2] = {na, nb};
+    const int widths[2] = {NA, NB};
+    int n0 = 0;
+    for (int i = 0; i < 2; ++i) {
+      const float* Wi = W(names[i] + ".kernel");
+      __nv_bfloat16* Wti = L.Wt + static_cast<size_t>(n0) * L.ldw;
+      pack_weight_bf16(Wi, Wti, K, widths[i], L.ldw, 0, fold ? fold->gamma : nullptr);
+      if (fold) ln_fold_consts(Wi, Wti, L.ldw, fold->beta, nullptr, c + n0, c + L.N + n0, K, widths[i], 0);
+      n0 += widths[i];
+    }
+    return L;
+  }
   Norm make_norm(const std::string& n, int D) { return Norm{W(n + ".gamma"), W(n + ".beta"), D}; }
   // fold_ok: the layer is only ever used as a self-attention layer (its LayerNorms feed nothing but GEMMs)
   LayerW make_layer(const std::string& pre, int dim, int heads, int dh, int mlp, int kind, bool fold_ok = true) {
@@ -324,7 +353,10 @@ struct vb_handle {
     const Norm* fa = l.folded ? &l.attn_norm : nullptr;
     const Norm* ff = l.folded ? &l.ff_norm : nullptr;
     if (kind == VB_KIND_VIT || kind == VB_KIND_DEEPVIT) { l.fused_qkv = true; l.to_qkv = make_linear(pre + "to_qkv", dim, 3 * inner, false, fa); }
-    else { l.to_q = make_linear(pre + "to_q", dim, inner, false, fa); l.to_kv = make_linear(pre + "to_kv", dim, 2 * inner, false, fa); }
+    else if (bf16() && fold_ok && dim % 8 == 0) {   // self-attention only: q and kv read the same rows -> one GEMM
+      l.fused_qkv = true;
+      l.to_qkv = make_linear_pair(pre + "to_q", inner, pre + "to_kv", 2 * inner, dim, fa);
+    } else { l.to_q = make_linear(pre + "to_q", dim, inner, false, fa); l.to_kv = make_linear(pre + "to_kv", dim, 2 * inner, false, fa); }
     if (kind == VB_KIND_DEEPVIT) { l.variant = 1; l.mix_a = W(pre + "reattn_weights"); l.reattn_norm = make_norm(pre + "reattn_norm", heads); }
     if (kind == VB_KIND_CAIT) {
       l.variant = 2; l.mix_a = W(pre + "mix_pre"); l.mix_b = W(pre + "mix_post");

@@ -404,7 +404,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-    if (lane == 0) bulk_wait_group<0>();   // all output bytes are globally visible before exit
+    if (lane == 0) bulk_wait_group_read<0>();   // the slab must outlive the store's reads; the writes drain before the grid completes
   }
 
   tcgen05_fence_before();
