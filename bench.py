@@ -112,6 +112,19 @@ def oracle_cfg(c):
     return oracle.make_config(c["kind"], **kw)
 
 
+def ncu_dram_traffic(config):
+    """DRAM bytes (read + write) per GEMM launch from the committed ncu capture of this bench command, or None.
+    The number is from a profiler run (cold caches, serialised kernels); it is reported next to the live timing, never
+    measured inside it."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", f"r01_dram_traffic_{config}.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return d["gemm_class"]["dram_bytes_per_launch"], os.path.relpath(path, os.path.dirname(os.path.abspath(__file__)))
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
 def usable_cores():
     """Host threads this process may really use: scheduler affinity capped by the cgroup CPU quota (a container that
     sees 128 logical CPUs but owns a fraction of them thrashes with 128 torch threads)."""
@@ -280,8 +293,10 @@ def run_ours(args, c):
     if g["launches"] > 0 and g["ms"] > 0:
         achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
+        traffic, traffic_src = ncu_dram_traffic(args.config)
         roof = dict(bound="tensor", kernel="gemm_bf16_kernel (tcgen05, all epilogue variants)", achieved=achieved, peak=peak,
-                    unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                    unit="TFLOP/s", frac=achieved / peak, traffic=traffic, traffic_source=traffic_src,
+                    algorithmic_bytes_per_launch=g["bytes"] / g["launches"],
                     peak_source=f"{peaks['source']} MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step); "
                                 f"burst peak {peaks['bf16_tflops']}",
                     launches=g["launches"], avg_launch_ms=g["ms"] / g["launches"],

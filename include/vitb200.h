@@ -91,6 +91,14 @@ VB_API int vb_forward(vb_handle* h, const float* img, int32_t img_mem, int32_t b
 VB_API int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_mem, int32_t batch, int32_t n,
                       float* out, int32_t out_mem, void* stream);
 
+/* DistillMixin.call with a distillation token (reference: distill.py:16-45, DistillableViT distill.py:47-58; ViT only):
+ * patch embedding + cls + positions, the token appended as the LAST row, the transformer over n + 2 rows, then
+ * logits = mlp_head(pool(x[:, :-1])) and distill_out = x[:, -1].
+ * distill_token: HOST float32 [dim] (the caller's trainable variable, distill.py:133).  logits [batch, num_classes] and
+ * distill_out [batch, dim] live in `out_mem` memory.  img as in vb_forward. */
+VB_API int vb_forward_distill(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w,
+                       const float* distill_token, float* logits, float* distill_out, int32_t out_mem, void* stream);
+
 /* Kernels launched by this handle's most recent forward call. */
 VB_API int64_t vb_last_launch_count(vb_handle* h);
 

@@ -209,6 +209,22 @@ def forward(img, weights, cfg, dtype=np.float64):
     raise ValueError(kind)
 
 
+def forward_distill(img, distill_token, weights, cfg, dtype=np.float64):
+    """DistillMixin.call with a distillation token (distill.py:16-45) on a ViT: returns (logits, distill_tokens)."""
+    w = {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}
+    img = np.asarray(img, dtype=dtype)
+    x = patch_embed(img, w, "patch", cfg["patch_h"], cfg["patch_w"])                       # :18
+    b, n, d = x.shape
+    x = np.concatenate([np.broadcast_to(w["cls_token"], (b, 1, d)), x], axis=1)             # :21-22
+    x = x + w["pos_embedding"][:, :n + 1]                                                   # :23
+    tok = np.broadcast_to(np.asarray(distill_token, dtype=dtype).reshape(1, 1, d), (b, 1, d))
+    x = np.concatenate([x, tok], axis=1)                                                    # :26-27
+    x = transformer_vit(x, w, cfg)                                                          # :29 (_attend, dropout 0)
+    x, dist = x[:, :-1], x[:, -1]                                                           # :32
+    x = x.mean(axis=1) if cfg["pool"] == "mean" else x[:, 0]                                # :34-37
+    return dense(layer_norm(x, w, "head_norm"), w, "head"), dist                            # :39-42
+
+
 def transformer_tokens(x, weights, cfg, dtype=np.float64):
     """`model.transformer(tokens)` for ViT/DeepViT with arbitrary n (mae.py:69, simmim.py:116)."""
     w = {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}

@@ -89,6 +89,37 @@ def test_transformer_tokens_entry(lib, precision):
         assert (np.abs(got - ref) <= 5e-2 + 3e-2 * np.abs(ref)).all()
 
 
+@pytest.mark.parametrize("pool", ["cls", "mean"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_distillable_vit_forward(lib, precision, pool):
+    # DistillMixin.call (distill.py:16-45): token appended as the last row, (logits, distill_tokens) returned
+    from oracle import spec_numpy
+    from vit_tensorflow_b200 import DistillableViT
+    cfg = dict(cfg_of("vit_small"))
+    cfg["pool"] = pool
+    w = oracle.stress_weights(cfg, 4)
+    kw = dict(image_size=(cfg["image_h"], cfg["image_w"]), patch_size=(cfg["patch_h"], cfg["patch_w"]), num_classes=cfg["num_classes"],
+              dim=cfg["dim"], depth=cfg["depth"], heads=cfg["heads"], mlp_dim=cfg["mlp_dim"], pool=pool, dim_head=cfg["dim_head"])
+    m = DistillableViT(precision=precision, **kw)
+    m.set_weights_dict(w)
+    img = oracle.make_image(cfg, 3, 8)
+    tok = np.random.default_rng(3).standard_normal((1, 1, cfg["dim"])).astype(np.float32)
+    logits, dist = m(img, tok, training=False)
+    ref_l, ref_d = spec_numpy.forward_distill(img, tok, w, cfg)
+    assert logits.shape == (3, cfg["num_classes"]) and dist.shape == (3, cfg["dim"])
+    if precision == "fp32":
+        np.testing.assert_allclose(logits, ref_l, rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(dist, ref_d, rtol=1e-3, atol=1e-4)
+    else:
+        assert (np.abs(logits - ref_l) <= BF16_ATOL + BF16_RTOL * np.abs(ref_l)).all()
+        assert (np.abs(dist - ref_d) <= BF16_ATOL + BF16_RTOL * np.abs(ref_d)).all()
+    # without a token the call is the plain ViT forward
+    plain = m(img, training=False)
+    refp = oracle.forward_numpy(img, w, cfg)
+    tol = (1e-4 + 1e-3 * np.abs(refp)) if precision == "fp32" else (BF16_ATOL + BF16_RTOL * np.abs(refp))
+    assert (np.abs(plain - refp) <= tol).all()
+
+
 def test_batch_independence_and_determinism(lib):
     """Images are independent (no cross-sample op): logits of a batch equal logits of its halves, bit for bit,
     and repeated calls are bit-identical (what the data-parallel sharding relies on)."""

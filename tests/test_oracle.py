@@ -71,6 +71,27 @@ def test_transformer_tokens_any_n():
     np.testing.assert_allclose(b, a, rtol=1e-4, atol=2e-5)
 
 
+def test_distill_forward_reduces_to_vit_and_tokens():
+    """distill.py:16-45 restated: logits of the distill call equal mlp_head over the first n+1 rows of the transformer
+    run on [cls; patches; token]; the two oracle restatements of the pieces agree."""
+    cfg = cfg_of("vit_small")
+    w = oracle.stress_weights(cfg, 1)
+    img = oracle.make_image(cfg, 2, 5)
+    tok = np.random.default_rng(1).standard_normal((1, 1, cfg["dim"]))
+    logits, dist = spec_numpy.forward_distill(img, tok, w, cfg)
+    wd = {k: np.asarray(v, np.float64) for k, v in w.items()}
+    x = spec_numpy.patch_embed(np.asarray(img, np.float64), wd, "patch", cfg["patch_h"], cfg["patch_w"])
+    b, n, d = x.shape
+    x = np.concatenate([np.broadcast_to(wd["cls_token"], (b, 1, d)), x], 1) + wd["pos_embedding"][:, :n + 1]
+    x = np.concatenate([x, np.broadcast_to(tok, (b, 1, d))], 1)
+    y = ref_torch.TorchReference(w, cfg).transformer(x.astype(np.float32))
+    np.testing.assert_allclose(dist, y[:, -1], rtol=1e-4, atol=5e-5)
+    assert logits.shape == (2, cfg["num_classes"]) and np.isfinite(logits).all()
+    # a zero-influence check: the token changes the logits (it attends with every row)
+    l2, _ = spec_numpy.forward_distill(img, tok * 2.0, w, cfg)
+    assert np.abs(l2 - logits).max() > 1e-6
+
+
 def test_config_asserts_match_reference_messages():
     with pytest.raises(AssertionError, match="Image dimensions must be divisible by the patch size."):
         oracle.make_config("vit", image_size=30, patch_size=16, num_classes=2, dim=8, depth=1, heads=1, mlp_dim=8)

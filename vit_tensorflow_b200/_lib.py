@@ -43,6 +43,8 @@ SIGNATURES = {
     "vb_finalize": (C.c_int, [C.c_void_p]),
     "vb_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
     "vb_forward_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]),
+    "vb_forward_distill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_int32, C.c_void_p]),
     "vb_last_launch_count": (C.c_int64, [C.c_void_p]),
     "vb_profile_enable": (C.c_int, [C.c_void_p, C.c_int32]),
     "vb_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), _i64p, C.c_int32]),

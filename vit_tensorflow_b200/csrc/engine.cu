@@ -132,7 +132,7 @@ struct vb_handle {
   std::map<std::string, int> windex;
   std::vector<std::unique_ptr<DevMem>> owned;
   Arena arena;
-  DevMem img_dev, logits_dev, tok_dev;
+  DevMem img_dev, logits_dev, tok_dev, tokens_in, tokens_out;
   long long last_launches = 0;
 
   // optional per-kernel-class timing: CUDA events recorded on the launch stream around each call
@@ -674,6 +674,33 @@ struct vb_handle {
     }
   }
 
+  // DistillMixin.call (distill.py:16-45) on top of a ViT: embed -> append the distillation token as the LAST row ->
+  // transformer over n + 2 rows -> head on the first n + 1 rows, and the last row returned as is.
+  template <typename T>
+  void distill_impl(const float* img, int B, int H, int Wd, const float* distill_token, float* logits, float* distill_out, cudaStream_t s) {
+    const vb_config& c = cfg;
+    VB_CHECK(c.kind == VB_KIND_VIT, "vb_forward_distill supports ViT (distill.py:47 DistillableViT)");
+    arena.reset();
+    int rows = 0;
+    T* E = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s, nullptr);
+    const int rd = rows + 1;
+    T* X = arena.get<T>(static_cast<size_t>(B) * rd * c.dim);
+    copy_tokens<T>(E, rows, 0, X, rd, 0, rows, B, c.dim, s);
+    T* last = X + static_cast<size_t>(rows) * c.dim;                 // row `rows` of image 0; image pitch rd rows
+    broadcast_row<T>(distill_token, last, rd, B, c.dim, s);
+    float* stats = (bf16() && c.dim % 64 == 0 && getenv("VB_NO_LN_FOLD") == nullptr) ? arena.get<float>(static_cast<size_t>(B) * rd * (c.dim / 64) * 2) : nullptr;
+    bool sv = false;
+    for (const auto& l : layers) layer_self<T>(X, B, rd, c.dim, l, s, stats, &sv);
+    T* Xh = arena.get<T>(static_cast<size_t>(B) * rows * c.dim);     // x[:, :-1]
+    copy_tokens<T>(X, rd, 0, Xh, rows, 0, rows, B, c.dim, s);
+    classify<T>(Xh, rows, c.dim, head_norm, head, B, c.pool == VB_POOL_MEAN, logits, false, s);
+    T* D = arena.get<T>(static_cast<size_t>(B) * c.dim);             // x[:, -1]
+    copy_tokens<T>(X, rd, rows, D, 1, 0, 1, B, c.dim, s);
+    const long long count = static_cast<long long>(B) * c.dim;
+    if (sizeof(T) == 4) VB_CUDA(cudaMemcpyAsync(distill_out, D, count * 4, cudaMemcpyDeviceToDevice, s));
+    else convert<__nv_bfloat16, float>(reinterpret_cast<const __nv_bfloat16*>(D), distill_out, count, s);
+  }
+
   template <typename T>
   void tokens_impl(const float* tok, int B, int n, float* out, cudaStream_t s) {
     VB_CHECK(cfg.kind == VB_KIND_VIT || cfg.kind == VB_KIND_DEEPVIT, "vb_forward_tokens supports ViT / DeepViT");
@@ -953,6 +980,49 @@ int vb_forward(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, i
     h->last_launches = launch_counter() - before;
     if (logits_mem == VB_MEM_HOST) {
       VB_CUDA(cudaMemcpyAsync(logits, out_d, out_bytes, cudaMemcpyDeviceToHost, s));
+      VB_CUDA(cudaStreamSynchronize(s));
+    }
+  });
+}
+
+int vb_forward_distill(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w,
+                       const float* distill_token, float* logits, float* distill_out, int32_t out_mem, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && img != nullptr && distill_token != nullptr && logits != nullptr && distill_out != nullptr,
+             "vb_forward_distill: null argument");
+    VB_CHECK(h->finalized, "vb_forward_distill: call vb_finalize after setting the weights");
+    VB_CHECK(batch > 0 && img_h > 0 && img_w > 0, "vb_forward_distill: bad batch / image size");
+    VB_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long before = launch_counter();
+    const int dim = h->cfg.dim;
+    const size_t img_bytes = static_cast<size_t>(batch) * img_h * img_w * h->cfg.channels * sizeof(float);
+    const size_t log_bytes = static_cast<size_t>(batch) * h->cfg.num_classes * sizeof(float);
+    const size_t dis_bytes = static_cast<size_t>(batch) * dim * sizeof(float);
+    const float* img_d = img;
+    if (img_mem == VB_MEM_HOST) {
+      h->img_dev.ensure(img_bytes);
+      VB_CUDA(cudaMemcpyAsync(h->img_dev.p, img, img_bytes, cudaMemcpyHostToDevice, s));
+      img_d = static_cast<const float*>(h->img_dev.p);
+    }
+    // the distillation token is always a host vector of `dim` floats (a trainable variable of the caller, distill.py:133)
+    h->tokens_in.ensure(static_cast<size_t>(dim) * sizeof(float));
+    VB_CUDA(cudaMemcpyAsync(h->tokens_in.p, distill_token, static_cast<size_t>(dim) * sizeof(float), cudaMemcpyHostToDevice, s));
+    float* log_d = logits;
+    float* dis_d = distill_out;
+    if (out_mem == VB_MEM_HOST) {
+      h->logits_dev.ensure(log_bytes);
+      h->tokens_out.ensure(dis_bytes);
+      log_d = static_cast<float*>(h->logits_dev.p);
+      dis_d = static_cast<float*>(h->tokens_out.p);
+    }
+    const float* tok_d = static_cast<const float*>(h->tokens_in.p);
+    if (h->bf16()) h->distill_impl<__nv_bfloat16>(img_d, batch, img_h, img_w, tok_d, log_d, dis_d, s);
+    else h->distill_impl<float>(img_d, batch, img_h, img_w, tok_d, log_d, dis_d, s);
+    h->last_launches = launch_counter() - before;
+    if (out_mem == VB_MEM_HOST) {
+      VB_CUDA(cudaMemcpyAsync(logits, log_d, log_bytes, cudaMemcpyDeviceToHost, s));
+      VB_CUDA(cudaMemcpyAsync(distill_out, dis_d, dis_bytes, cudaMemcpyDeviceToHost, s));
       VB_CUDA(cudaStreamSynchronize(s));
     }
   });

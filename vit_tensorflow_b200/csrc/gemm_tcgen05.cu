@@ -106,6 +106,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // trace role 3 = kernel phases seen by thread 0 of CTA 0: 90 entry, 91 set-up done, 92 predecessor grid complete, 99 exit
+  auto phase_mark = [&](int slot, int tag) {
+    if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { dbg[3 * 512 + 2 * slot] = tag; dbg[3 * 512 + 2 * slot + 1] = clock64(); }
+  };
+  phase_mark(0, 90);
   constexpr int TM = BM * CG;                                      // rows per tile (per CTA pair when CG == 2)
   const int tiles_m = (M + TM - 1) / TM;
   const int tiles_n = (N + BN - 1) / BN;
@@ -140,8 +145,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (CG == 2) cluster_sync_all();                                 // peer barriers are initialised before any remote signal
   tcgen05_fence_after();
   // Everything above overlapped the previous kernel's tail (PDL); from here on we touch its outputs.
+  phase_mark(1, 91);
   pdl_wait();
   pdl_launch_dependents();
+  phase_mark(2, 92);
   // optional timeline trace (VB_GEMM_TRACE=path through vb_op_linear): CTA 0 records (tag, clock) pairs per role
   int dbg_n = 0;
   auto trace = [&](int role, int tag) {
@@ -414,6 +421,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     tcgen05_fence_after();
     if (CG == 2) tmem_dealloc_cg2<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
+  phase_mark(3, 99);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

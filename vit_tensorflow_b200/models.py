@@ -240,6 +240,38 @@ class ViT(_EngineModel):
         self.transformer = _Transformer(self)
 
 
+class DistillableViT(ViT):
+    """distill.py:47-58 (DistillMixin.call distill.py:16-45): a ViT whose call takes an optional distillation token
+    `[1, 1, dim]`; with it the call returns `(logits, distill_tokens [b, dim])`, without it plain ViT logits.
+    Forward only -- DistillWrapper's losses (distill.py:100-170) stay with the caller."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.args, self.kwargs = args, kwargs
+        self.dim, self.num_classes = kwargs["dim"], kwargs["num_classes"]
+
+    def __call__(self, img, distill_token=None, training=True):
+        if distill_token is None:
+            return super().__call__(img, training=training)
+        self._check_training(training)
+        self._finalize()
+        x = np.ascontiguousarray(img, dtype=np.float32)
+        if x.ndim != 4 or x.shape[3] != 3:
+            raise ValueError("img must be NHWC float [b, H, W, 3]")
+        tok = np.ascontiguousarray(distill_token, dtype=np.float32).reshape(-1)
+        if tok.size != self.dim:
+            raise ValueError(f"distill_token must hold dim = {self.dim} values, got shape {np.shape(distill_token)}")
+        b, h, w, _ = x.shape
+        logits = np.empty((b, self.num_classes), np.float32)
+        dist = np.empty((b, self.dim), np.float32)
+        _lib.check(self._lib.vb_forward_distill(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, h, w,
+                                                tok.ctypes.data_as(C.c_void_p), logits.ctypes.data_as(C.c_void_p),
+                                                dist.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
+        return logits, dist
+
+    call = __call__
+
+
 class DeepViT(ViT):
     """deepvit.py:112-157 (integer image/patch sizes only, :117-118)."""
     _kind = "deepvit"
