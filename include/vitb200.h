@@ -6,6 +6,7 @@
  *     DeepViT(...)(img)              vit_tensorflow/deepvit.py:113-114,139-157
  *     CaiT(...)(img)                 vit_tensorflow/cait.py:156-157,180-194
  *     CrossViT(...)(img)             vit_tensorflow/cross_vit.py:233-253,290-303
+ *     parallel_vit.ViT(...)(img)     vit_tensorflow/parallel_vit.py:120-133,167-185   
  * and this header is what the Python host classes (vit_tensorflow_b200/*.py) bind with ctypes.
  * Plain pointers and sizes only; no torch / C++ types cross the boundary.
  *
@@ -25,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 1
+#define VB_ABI_VERSION 2
 #if defined(__GNUC__)
 #define VB_API __attribute__((visibility("default")))
 #else
@@ -34,12 +35,12 @@ extern "C" {
 
 typedef struct vb_handle vb_handle;
 
-enum { VB_KIND_VIT = 0, VB_KIND_DEEPVIT = 1, VB_KIND_CAIT = 2, VB_KIND_CROSSVIT = 3 };
+enum { VB_KIND_VIT = 0, VB_KIND_DEEPVIT = 1, VB_KIND_CAIT = 2, VB_KIND_CROSSVIT = 3, VB_KIND_PARALLEL_VIT = 4 };
 enum { VB_PRECISION_FP32 = 0, VB_PRECISION_BF16 = 1 };
 enum { VB_POOL_CLS = 0, VB_POOL_MEAN = 1 };
 enum { VB_MEM_HOST = 0, VB_MEM_DEVICE = 1 };
 
-/* Constructor kwargs of the four reference classes, flattened.  Unused fields are ignored per kind. */
+/* Constructor kwargs of the reference classes, flattened.  Unused fields are ignored per kind. */
 typedef struct vb_config {
   int32_t struct_size;            /* sizeof(vb_config), ABI guard */
   int32_t kind;                   /* VB_KIND_* */
@@ -58,6 +59,7 @@ typedef struct vb_config {
   int32_t lg_patch_size, lg_enc_depth, lg_enc_heads, lg_enc_mlp_dim, lg_enc_dim_head;
   int32_t cross_attn_depth, cross_attn_heads, cross_attn_dim_head;
   int32_t cross_depth;            /* CrossViT `depth`: number of multi-scale blocks */
+  int32_t parallel_branches;      /* parallel ViT `num_parallel_branches` (parallel_vit.py:130); ignored by the other kinds */
 } vb_config;
 
 VB_API int vb_abi_version(void);

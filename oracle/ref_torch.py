@@ -103,12 +103,29 @@ def _transformer_vit(x, w, cfg):
     return x
 
 
+def _transformer_parallel(x, w, cfg):
+    # parallel_vit.py:114-117, Parallel :41-42
+    for L in range(cfg["depth"]):
+        pres = [f"layers.{L}.branch{i}." for i in range(cfg["num_parallel_branches"])]
+        a = None
+        for p in pres:
+            y = _attn_vit(_ln(x, w, p + "attn_norm"), w, p, cfg["heads"], cfg["dim_head"], False)
+            a = y if a is None else a + y
+        x = a + x
+        f = None
+        for p in pres:
+            y = _mlp(_ln(x, w, p + "ff_norm"), w, p)
+            f = y if f is None else f + y
+        x = f + x
+    return x
+
+
 def _forward_vit(img, w, cfg):
-    # vit.py:159-177
+    # vit.py:159-177 / parallel_vit.py:167-185
     x = _linear(_im2col(img, cfg["patch_h"], cfg["patch_w"]), w, "patch")
     b, n, d = x.shape
     x = torch.cat([w["cls_token"].expand(b, 1, d), x], dim=1) + w["pos_embedding"][:, :n + 1]
-    x = _transformer_vit(x, w, cfg)
+    x = _transformer_parallel(x, w, cfg) if cfg["kind"] == "parallel_vit" else _transformer_vit(x, w, cfg)
     x = x.mean(dim=1) if cfg["pool"] == "mean" else x[:, 0]
     return _linear(_ln(x, w, "head_norm"), w, "head")
 
@@ -183,7 +200,7 @@ class TorchReference:
     def __call__(self, img):
         x = torch.as_tensor(img).to(self.dtype)
         kind = self.cfg["kind"]
-        if kind in ("vit", "deepvit"):
+        if kind in ("vit", "deepvit", "parallel_vit"):
             y = _forward_vit(x, self.w, self.cfg)
         elif kind == "cait":
             y = _forward_cait(x, self.w, self.cfg)

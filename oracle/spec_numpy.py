@@ -113,14 +113,23 @@ def transformer_vit(x, w, cfg, prefix="layers."):
     return x
 
 
+def transformer_parallel(x, w, cfg):
+    """parallel_vit.py:114-117 with Parallel :41-42: every branch has its own PreNorm; branch outputs are summed."""
+    for L in range(cfg["depth"]):
+        pres = [f"layers.{L}.branch{i}." for i in range(cfg["num_parallel_branches"])]
+        x = sum(attention_vit(layer_norm(x, w, p + "attn_norm"), w, p, cfg["heads"], cfg["dim_head"]) for p in pres) + x
+        x = sum(mlp(layer_norm(x, w, p + "ff_norm"), w, p) for p in pres) + x
+    return x
+
+
 def forward_vit(img, w, cfg):
-    """vit.py:159-177 / deepvit.py:139-157."""
+    """vit.py:159-177 / deepvit.py:139-157 / parallel_vit.py:167-185."""
     x = patch_embed(img, w, "patch", cfg["patch_h"], cfg["patch_w"])
     b, n, _ = x.shape
     cls = np.broadcast_to(w["cls_token"], (b, 1, x.shape[-1]))
     x = np.concatenate([cls, x], axis=1)
     x = x + w["pos_embedding"][:, :n + 1]
-    x = transformer_vit(x, w, cfg)
+    x = transformer_parallel(x, w, cfg) if cfg["kind"] == "parallel_vit" else transformer_vit(x, w, cfg)
     x = x.mean(axis=1) if cfg["pool"] == "mean" else x[:, 0]
     return dense(layer_norm(x, w, "head_norm"), w, "head")
 
@@ -200,7 +209,7 @@ def forward(img, weights, cfg, dtype=np.float64):
     w = {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}
     img = np.asarray(img, dtype=dtype)
     kind = cfg["kind"]
-    if kind in ("vit", "deepvit"):
+    if kind in ("vit", "deepvit", "parallel_vit"):
         return forward_vit(img, w, cfg)
     if kind == "cait":
         return forward_cait(img, w, cfg)

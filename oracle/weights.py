@@ -6,6 +6,7 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows the reference constructor
   CaiT     vit_tensorflow/cait.py:155-178 (+ LayerScale :33-45, Attention :85-105)
   CrossViT vit_tensorflow/cross_vit.py:232-288 (+ ImageEmbedder :199-217,
            Transformer :95-107, ProjectInOut :118-126, CrossTransformer :141-150)
+  parallel ViT  vit_tensorflow/parallel_vit.py:120-165 (+ Parallel :36-42, Transformer :99-117)
 
 Weight layouts are the Keras layouts: Dense kernel ``[in, out]``, bias ``[out]``,
 LayerNormalization gamma/beta ``[dim]``.
@@ -23,8 +24,10 @@ def _pair(t):
 def make_config(kind: str, **kw) -> dict:
     """Normalise constructor kwargs to a flat config dict, applying the reference defaults."""
     kind = kind.lower()
-    if kind in ("vit", "deepvit"):
+    if kind in ("vit", "deepvit", "parallel_vit"):
         cfg = dict(kind=kind, pool="cls", dim_head=64, channels=3)
+        if kind == "parallel_vit":
+            cfg["num_parallel_branches"] = 2                          # parallel_vit.py:130
         cfg.update(kw)
         ih, iw = _pair(cfg["image_size"])
         ph, pw = _pair(cfg["patch_size"])
@@ -104,14 +107,20 @@ def weight_specs(cfg: dict) -> "collections.OrderedDict[str, tuple]":
     specs: collections.OrderedDict = collections.OrderedDict()
     kind = cfg["kind"]
     C = cfg["channels"]
-    if kind in ("vit", "deepvit"):
+    if kind in ("vit", "deepvit", "parallel_vit"):
         dim = cfg["dim"]
         pd = cfg["patch_h"] * cfg["patch_w"] * C
         specs["pos_embedding"] = ((1, cfg["num_patches"] + 1, dim), "normal")
         specs["cls_token"] = ((1, 1, dim), "normal")
         _dense(specs, "patch", pd, dim)
         for L in range(cfg["depth"]):
-            _vit_layer(specs, f"layers.{L}.", dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], kind=kind)
+            if kind == "parallel_vit":
+                # branch i = (Parallel attention fn i, Parallel feed-forward fn i) of layer L (parallel_vit.py:109-112):
+                # Keras path model.transformer.layers[L][0].fns[i] / [L][1].fns[i]
+                for i in range(cfg["num_parallel_branches"]):
+                    _vit_layer(specs, f"layers.{L}.branch{i}.", dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], kind="vit")
+            else:
+                _vit_layer(specs, f"layers.{L}.", dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], kind=kind)
         _ln(specs, "head_norm", dim)
         _dense(specs, "head", dim, cfg["num_classes"])
     elif kind == "cait":
@@ -223,12 +232,12 @@ def flops_per_image(cfg: dict) -> float:
     """Algorithmic FLOPs (2*MAC over every matmul at the true n), SURVEY.md App. C."""
     kind = cfg["kind"]
     C = cfg["channels"]
-    if kind in ("vit", "deepvit"):
+    if kind in ("vit", "deepvit", "parallel_vit"):
         n_p, dim = cfg["num_patches"], cfg["dim"]
         n = n_p + 1
         f = 2 * n_p * cfg["patch_h"] * cfg["patch_w"] * C * dim
-        po = not (kind == "vit" and cfg["heads"] == 1 and cfg["dim_head"] == dim)
-        f += cfg["depth"] * _layer_flops(n, n, dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"],
+        po = not (kind != "deepvit" and cfg["heads"] == 1 and cfg["dim_head"] == dim)
+        f += cfg["depth"] * cfg.get("num_parallel_branches", 1) * _layer_flops(n, n, dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"],
                                          mixes=1 if kind == "deepvit" else 0, project_out=po)
         f += 2 * dim * cfg["num_classes"]
         return float(f)

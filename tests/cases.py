@@ -19,6 +19,10 @@ SMALL = {
                            lg_patch_size=16, sm_enc_depth=1, lg_enc_depth=2, sm_enc_heads=2, lg_enc_heads=2,
                            sm_enc_mlp_dim=64, lg_enc_mlp_dim=128, sm_enc_dim_head=32, lg_enc_dim_head=32,
                            cross_attn_depth=2, cross_attn_heads=2, cross_attn_dim_head=32, depth=2),
+    "parallel_small": dict(kind="parallel_vit", image_size=64, patch_size=16, num_classes=10, dim=64, depth=2, heads=4, mlp_dim=128,
+                           dim_head=16),
+    "parallel_three_noproj": dict(kind="parallel_vit", image_size=32, patch_size=8, num_classes=5, dim=64, depth=2, heads=1,
+                                  mlp_dim=64, dim_head=64, num_parallel_branches=3, pool="mean"),
     "crossvit_samedim": dict(kind="crossvit", image_size=32, num_classes=6, sm_dim=64, lg_dim=64, sm_patch_size=8,
                              lg_patch_size=16, sm_enc_depth=1, lg_enc_depth=1, sm_enc_heads=2, lg_enc_heads=2,
                              sm_enc_mlp_dim=64, lg_enc_mlp_dim=64, sm_enc_dim_head=32, lg_enc_dim_head=32,
@@ -28,6 +32,7 @@ SMALL = {
 # Mid-size bf16 cases exercising the tcgen05 kernels at the real head / sequence geometry (n = 197, dh = 64).
 MID = {
     "vit_mid": dict(kind="vit", image_size=224, patch_size=16, num_classes=1000, dim=256, depth=2, heads=4, mlp_dim=512),
+    "parallel_mid": dict(kind="parallel_vit", image_size=224, patch_size=16, num_classes=100, dim=256, depth=2, heads=4, mlp_dim=512),
     "deepvit_mid": dict(kind="deepvit", image_size=224, patch_size=16, num_classes=100, dim=256, depth=2, heads=4, mlp_dim=512),
     "cait_mid": dict(kind="cait", image_size=224, patch_size=16, num_classes=100, dim=192, depth=2, cls_depth=2, heads=4,
                      mlp_dim=384, dim_head=48),

@@ -7,6 +7,6 @@ hand-written sm_100a CUDA in `libvitb200.so` (sources under `csrc/`, C-ABI in `i
 Importing the package does not load the library; constructing a model does, and fails loudly when the library
 or a B200 is missing -- there is no CPU / PyTorch fallback.
 """
-from .models import ViT, DeepViT, CaiT, CrossViT, DistillableViT, from_config, pair  # noqa: F401
+from .models import ViT, DeepViT, CaiT, CrossViT, DistillableViT, ParallelViT, from_config, pair  # noqa: F401
 
-__all__ = ["ViT", "DeepViT", "CaiT", "CrossViT", "DistillableViT", "from_config"]
+__all__ = ["ViT", "DeepViT", "CaiT", "CrossViT", "DistillableViT", "ParallelViT", "from_config"]

@@ -11,7 +11,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VB_LIB_PATH") or os.path.join(_HERE, "libvitb200.so")   # VB_LIB_PATH: developer A/B builds
 
-KIND = {"vit": 0, "deepvit": 1, "cait": 2, "crossvit": 3}
+KIND = {"vit": 0, "deepvit": 1, "cait": 2, "crossvit": 3, "parallel_vit": 4}
 PRECISION = {"fp32": 0, "float32": 0, "bf16": 1, "bfloat16": 1}
 MEM_HOST, MEM_DEVICE = 0, 1
 
@@ -23,7 +23,7 @@ class VbConfig(C.Structure):
         "sm_dim", "lg_dim",
         "sm_patch_size", "sm_enc_depth", "sm_enc_heads", "sm_enc_mlp_dim", "sm_enc_dim_head",
         "lg_patch_size", "lg_enc_depth", "lg_enc_heads", "lg_enc_mlp_dim", "lg_enc_dim_head",
-        "cross_attn_depth", "cross_attn_heads", "cross_attn_dim_head", "cross_depth")]
+        "cross_attn_depth", "cross_attn_heads", "cross_attn_dim_head", "cross_depth", "parallel_branches")]
 
 
 class VbError(RuntimeError):
@@ -70,7 +70,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.vb_abi_version() != 1:
+        if lib.vb_abi_version() != 2:
             raise VbError("libvitb200 ABI version mismatch")
         _lib = lib
     return _lib

@@ -222,12 +222,19 @@ struct vb_handle {
   void build_expected() {
     const vb_config& c = cfg;
     const int C = c.channels;
-    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT) {
+    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT || c.kind == VB_KIND_PARALLEL_VIT) {
       const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
       expect("pos_embedding", {1, np + 1, c.dim});
       expect("cls_token", {1, 1, c.dim});
       expect_dense("patch", c.patch_h * c.patch_w * C, c.dim);
-      for (int L = 0; L < c.depth; ++L) expect_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind);
+      for (int L = 0; L < c.depth; ++L) {
+        if (c.kind == VB_KIND_PARALLEL_VIT) {   // branch i = (attention fn i, feed-forward fn i) of layer L (parallel_vit.py:109-112)
+          for (int i = 0; i < c.parallel_branches; ++i)
+            expect_layer("layers." + std::to_string(L) + ".branch" + std::to_string(i) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_VIT);
+        } else {
+          expect_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind);
+        }
+      }
       expect_ln("head_norm", c.dim);
       expect_dense("head", c.dim, c.num_classes);
     } else if (c.kind == VB_KIND_CAIT) {
@@ -382,10 +389,17 @@ struct vb_handle {
     VB_CUDA(cudaSetDevice(device));
     owned.clear(); layers.clear(); cls_layers.clear(); xblocks.clear(); plans.clear(); embed_res.clear();
     const vb_config& c = cfg;
-    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT) {
+    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT || c.kind == VB_KIND_PARALLEL_VIT) {
       const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
       embed = make_embed("", c.patch_h, c.patch_w, c.dim, np + 1);
-      for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind));
+      for (int L = 0; L < c.depth; ++L) {
+        if (c.kind == VB_KIND_PARALLEL_VIT) {   // `layers` holds depth x parallel_branches entries, branches of a layer adjacent
+          for (int i = 0; i < c.parallel_branches; ++i)
+            layers.push_back(make_layer("layers." + std::to_string(L) + ".branch" + std::to_string(i) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_VIT));
+        } else {
+          layers.push_back(make_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind));
+        }
+      }
       head_norm = make_norm("head_norm", c.dim);
       head = make_linear_f32("head", c.dim, c.num_classes);
     } else if (c.kind == VB_KIND_CAIT) {
@@ -534,6 +548,55 @@ struct vb_handle {
     }
     feed_forward<T>(X, M, dim, l, Y, s, fold ? stats : nullptr, lnrows);
   }
+  // One parallel_vit layer (parallel_vit.py:114-117): x = sum_i attn_i(LN_i(x)) + x ; x = sum_i ff_i(LN'_i(x)) + x.
+  // Every branch reads the SAME x, so the sums accumulate in a second buffer through the residual epilogue of the
+  // branch's last GEMM (branch 0: res = x, out = acc; branch i > 0: res = out = acc); the attention half goes X -> Acc, the
+  // feed-forward half Acc -> X.  The branches' LayerNorms share the row statistics of x, so folding still applies.
+  template <typename T>
+  void layer_parallel(T* X, T* Acc, int B, int rows, int dim, const LayerW* br, int nbr, cudaStream_t s, float* stats, bool* stats_valid) {
+    const int M = B * rows, inner = br[0].heads * br[0].dim_head;
+    const bool fold = br[0].folded && stats != nullptr;
+    if (fold && !*stats_valid) { ensure_stats(X, dim, stats, M, s); *stats_valid = true; }
+    T* Y = arena.get<T>(static_cast<size_t>(M) * dim);
+    T* O = arena.get<T>(static_cast<size_t>(M) * inner);
+    T* QKV = arena.get<T>(static_cast<size_t>(M) * 3 * inner);
+    T* Hb = arena.get<T>(static_cast<size_t>(M) * br[0].fc1.N);
+    float* lnrows = fold ? arena.get<float>(static_cast<size_t>(M) * 2) : nullptr;
+    // ---- attention branches: X -> Acc
+    if (fold) finalize_stats(stats, lnrows, M, dim, s);
+    for (int i = 0; i < nbr; ++i) {
+      const LayerW& l = br[i];
+      const T* A = X;
+      Epi eq;
+      if (fold) { eq.ln_rows = lnrows; eq.bias = l.to_qkv.ln_c2; }
+      else { VB_CHECK(!l.folded, "internal: folded layer without statistics"); ln<T>(X, l.attn_norm, Y, M, dim, s); A = Y; }
+      linear<T>(A, dim, M, l.to_qkv, QKV, 3 * inner, eq, s);
+      attention<T>(QKV, 3 * inner, QKV + inner, 3 * inner, QKV + 2 * inner, 3 * inner, O, inner, B, rows, rows, l, s);
+      const bool last = i == nbr - 1;
+      if (l.project_out) {
+        Epi e; e.bias = l.to_out.bias; e.res = i == 0 ? X : Acc; e.ldr = dim;
+        if (fold && last) e.stats_out = stats;
+        linear<T>(O, inner, M, l.to_out, Acc, dim, e, s);
+      } else {                                               // parallel_vit.py:74: Identity out-projection (inner == dim)
+        if (i == 0) VB_CUDA(cudaMemcpyAsync(Acc, X, static_cast<size_t>(M) * dim * sizeof(T), cudaMemcpyDeviceToDevice, s));
+        add_tokens<T>(Acc, O, static_cast<long long>(M) * dim, s);
+        if (fold && last) ensure_stats(Acc, dim, stats, M, s);
+      }
+    }
+    // ---- feed-forward branches: Acc -> X
+    if (fold) finalize_stats(stats, lnrows, M, dim, s);
+    for (int i = 0; i < nbr; ++i) {
+      const LayerW& l = br[i];
+      const T* A = Acc;
+      Epi e1; e1.gelu = true;
+      if (fold) { e1.ln_rows = lnrows; e1.bias = l.fc1.ln_c2; }
+      else { ln<T>(Acc, l.ff_norm, Y, M, dim, s); A = Y; e1.bias = l.fc1.bias; }
+      linear<T>(A, dim, M, l.fc1, Hb, l.fc1.N, e1, s);
+      Epi e2; e2.bias = l.fc2.bias; e2.res = i == 0 ? Acc : X; e2.ldr = dim;
+      if (fold && i == nbr - 1) e2.stats_out = stats;
+      linear<T>(Hb, l.fc1.N, M, l.fc2, X, dim, e2, s);
+    }
+  }
   void finalize_stats(const float* stats, float* rows, int M, int dim, cudaStream_t s) {
     ProfScope ps(this, PROF_LN, 0.0, 8.0 * M * (dim / 64) + 8.0 * M, s);
     row_stats_finalize(stats, rows, M, dim / 64, dim, s);
@@ -629,6 +692,15 @@ struct vb_handle {
       T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s, &stats);
       bool sv = stats != nullptr;
       for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s, stats, &sv);
+      classify<T>(X, rows, c.dim, head_norm, head, B, c.pool == VB_POOL_MEAN, logits, false, s);
+    } else if (c.kind == VB_KIND_PARALLEL_VIT) {
+      int rows = 0;
+      float* stats = nullptr;
+      T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s, &stats);
+      bool sv = stats != nullptr;
+      T* Acc = arena.get<T>(static_cast<size_t>(B) * rows * c.dim);
+      for (int L = 0; L < c.depth; ++L)
+        layer_parallel<T>(X, Acc, B, rows, c.dim, &layers[static_cast<size_t>(L) * c.parallel_branches], c.parallel_branches, s, stats, &sv);
       classify<T>(X, rows, c.dim, head_norm, head, B, c.pool == VB_POOL_MEAN, logits, false, s);
     } else if (c.kind == VB_KIND_CAIT) {
       int rows = 0;
@@ -817,7 +889,8 @@ int guarded(vb_handle* h, F&& f) {
 
 void validate(const vb_config& c) {
   VB_CHECK(c.struct_size == static_cast<int32_t>(sizeof(vb_config)), "vb_config.struct_size mismatch (ABI)");
-  VB_CHECK(c.kind >= VB_KIND_VIT && c.kind <= VB_KIND_CROSSVIT, "unknown model kind");
+  VB_CHECK(c.kind >= VB_KIND_VIT && c.kind <= VB_KIND_PARALLEL_VIT, "unknown model kind");
+  VB_CHECK(c.kind != VB_KIND_PARALLEL_VIT || (c.parallel_branches >= 1 && c.parallel_branches <= 8), "num_parallel_branches must be in [1, 8]");
   VB_CHECK(c.precision == VB_PRECISION_FP32 || c.precision == VB_PRECISION_BF16, "unknown precision");
   VB_CHECK(c.channels > 0 && c.num_classes > 0 && c.image_h > 0 && c.image_w > 0, "bad image / class configuration");
   if (c.kind == VB_KIND_CROSSVIT) {

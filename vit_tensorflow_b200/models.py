@@ -240,6 +240,27 @@ class ViT(_EngineModel):
         self.transformer = _Transformer(self)
 
 
+class ParallelViT(_EngineModel):
+    """parallel_vit.py:120-185 (`parallel_vit.ViT`): every layer sums `num_parallel_branches` attention blocks and then as
+    many feed-forward blocks, each behind its own LayerNorm (Parallel parallel_vit.py:36-42, Transformer :99-117)."""
+    _kind = "parallel_vit"
+
+    def __init__(self, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, pool='cls', num_parallel_branches=2,
+                 dim_head=64, dropout=0.0, emb_dropout=0.0, *, precision="bf16", device=0, seed=None):
+        image_height, image_width = pair(image_size)
+        patch_height, patch_width = pair(patch_size)
+        assert image_height % patch_height == 0 and image_width % patch_width == 0, 'Image dimensions must be divisible by the patch size.'
+        assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
+        self.num_classes, self.pool, self.dim = num_classes, pool, dim
+        self._dropout_rates = (dropout, emb_dropout)
+        self._create(precision, device, image_h=image_height, image_w=image_width, patch_h=patch_height, patch_w=patch_width,
+                     num_classes=num_classes, dim=dim, depth=depth, heads=heads, dim_head=dim_head, mlp_dim=mlp_dim,
+                     pool=0 if pool == 'cls' else 1, parallel_branches=num_parallel_branches)
+        self.init_weights(seed)
+        self.pos_embedding = _Tensorish(self, "pos_embedding")
+        self.cls_token = _Tensorish(self, "cls_token")
+
+
 class DistillableViT(ViT):
     """distill.py:47-58 (DistillMixin.call distill.py:16-45): a ViT whose call takes an optional distillation token
     `[1, 1, dim]`; with it the call returns `(logits, distill_tokens [b, dim])`, without it plain ViT logits.
@@ -327,7 +348,7 @@ class CrossViT(_EngineModel):
 def from_config(cfg: dict, precision="bf16", device=0, seed=None):
     """Build a model from an oracle-style config dict (kind + reference kwargs)."""
     kw = {k: v for k, v in cfg.items() if k not in ("kind", "channels", "image_h", "image_w", "patch_h", "patch_w", "num_patches")}
-    cls = {"vit": ViT, "deepvit": DeepViT, "cait": CaiT, "crossvit": CrossViT}[cfg["kind"]]
+    cls = {"vit": ViT, "deepvit": DeepViT, "cait": CaiT, "crossvit": CrossViT, "parallel_vit": ParallelViT}[cfg["kind"]]
     if cfg["kind"] == "crossvit":
         kw.setdefault("dropout", 0.0)
         kw.setdefault("emb_dropout", 0.0)
