@@ -7,6 +7,9 @@
  *     CaiT(...)(img)                 vit_tensorflow/cait.py:156-157,180-194
  *     CrossViT(...)(img)             vit_tensorflow/cross_vit.py:233-253,290-303
  *     parallel_vit.ViT(...)(img)     vit_tensorflow/parallel_vit.py:120-133,167-185   
+ *     T2TViT(...)(img)               vit_tensorflow/t2t.py:50-54,96-116               
+ *     vit_with_patch_merger.ViT(...)(img)   vit_tensorflow/vit_with_patch_merger.py:134-146,174-185   (8f, f4)
+ *     efficient.ViT(...)(img)        vit_tensorflow/efficient.py:13-14,39-55 = vb_forward_embed -> caller's transformer -> vb_forward_head
  * and this header is what the Python host classes (vit_tensorflow_b200/*.py) bind with ctypes.
  * Plain pointers and sizes only; no torch / C++ types cross the boundary.
  *
@@ -26,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 2
+#define VB_ABI_VERSION 3
 #if defined(__GNUC__)
 #define VB_API __attribute__((visibility("default")))
 #else
@@ -35,7 +38,8 @@ extern "C" {
 
 typedef struct vb_handle vb_handle;
 
-enum { VB_KIND_VIT = 0, VB_KIND_DEEPVIT = 1, VB_KIND_CAIT = 2, VB_KIND_CROSSVIT = 3, VB_KIND_PARALLEL_VIT = 4 };
+enum { VB_KIND_VIT = 0, VB_KIND_DEEPVIT = 1, VB_KIND_CAIT = 2, VB_KIND_CROSSVIT = 3, VB_KIND_PARALLEL_VIT = 4,
+       VB_KIND_PATCH_MERGER_VIT = 5, VB_KIND_T2T_VIT = 6 };
 enum { VB_PRECISION_FP32 = 0, VB_PRECISION_BF16 = 1 };
 enum { VB_POOL_CLS = 0, VB_POOL_MEAN = 1 };
 enum { VB_MEM_HOST = 0, VB_MEM_DEVICE = 1 };
@@ -60,6 +64,12 @@ typedef struct vb_config {
   int32_t cross_attn_depth, cross_attn_heads, cross_attn_dim_head;
   int32_t cross_depth;            /* CrossViT `depth`: number of multi-scale blocks */
   int32_t parallel_branches;      /* parallel ViT `num_parallel_branches` (parallel_vit.py:130); ignored by the other kinds */
+  /* vit_with_patch_merger.ViT (vit_with_patch_merger.py:104-109,141-142) */
+  int32_t patch_merge_layer_index;   /* default(patch_merge_layer, depth // 2) - 1: merge AFTER this layer; outside [0, depth) = never */
+  int32_t patch_merge_num_tokens;
+  /* T2TViT `t2t_layers` (t2t.py:54): up to 4 (kernel_size, stride) soft-split layers; image_h == image_w, patch_* unused */
+  int32_t t2t_num_layers;
+  int32_t t2t_k0, t2t_s0, t2t_k1, t2t_s1, t2t_k2, t2t_s2, t2t_k3, t2t_s3;
 } vb_config;
 
 VB_API int vb_abi_version(void);
@@ -101,6 +111,35 @@ VB_API int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_m
 VB_API int vb_forward_distill(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w,
                        const float* distill_token, float* logits, float* distill_out, int32_t out_mem, void* stream);
 
+/* ---- the stages of <Model>.call on their own: the attribute surface the reference's wrappers and the
+ * injected-transformer shell use.  ViT / DeepViT / parallel ViT / CaiT / patch-merger ViT / T2TViT; not CrossViT. ----------- */
+
+/* Number of token rows vb_forward_embed produces for an img_h x img_w image (patches + cls where the model has one);
+ * negative on error. */
+VB_API int vb_embed_rows(vb_handle* h, int32_t img_h, int32_t img_w);
+
+/* Everything `call` does before `self.transformer` (vit.py:160-166, cait.py:181-184, t2t.py:97-103, efficient.py:40-45,
+ * vit_with_patch_merger.py:175-179): patch embedding (T2T: the whole tokens-to-token module), cls token, positions.
+ * tokens: float32 [batch, vb_embed_rows, dim]. */
+VB_API int vb_forward_embed(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w,
+                     float* tokens, int32_t tokens_mem, void* stream);
+
+/* Everything `call` does after `self.transformer` (vit.py:170-175, efficient.py:48-55): pooling (cls row / mean over
+ * the n rows, per the config) + mlp_head (LayerNorm, Dense).  tokens float32 [batch, n, dim] -> logits [batch, num_classes].
+ * With n == 1 this is `model.mlp_head(x)`. */
+VB_API int vb_forward_head(vb_handle* h, const float* tokens, int32_t tokens_mem, int32_t batch, int32_t n, float* logits,
+                    int32_t logits_mem, void* stream);
+
+/* `patch_embedding.layers[0]` (the einops Rearrange, vit.py:142; mae.py:37 `to_patch`): img -> float32
+ * [batch, num_patches, patch_h*patch_w*channels].  Not for T2TViT. */
+VB_API int vb_to_patch(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w,
+                float* patches, int32_t patches_mem, void* stream);
+
+/* `patch_embedding.layers[1]` / `.layers[-1]` (the Dense, vit.py:143; mae.py:37 `patch_to_emb`, mpp.py:200):
+ * patches float32 [rows, patch_dim] -> float32 [rows, dim] (patch_dim = the Dense's input width; T2T: the last soft split's). */
+VB_API int vb_patch_to_emb(vb_handle* h, const float* patches, int32_t patches_mem, int32_t rows, float* out, int32_t out_mem,
+                    void* stream);
+
 /* Kernels launched by this handle's most recent forward call. */
 VB_API int64_t vb_last_launch_count(vb_handle* h);
 
@@ -138,6 +177,11 @@ VB_API int vb_op_attention(int32_t precision, int32_t variant, const float* q, c
 /* LayerNorm over the last axis, eps 1e-3 (vit.py:18): x [M,D] -> out [M,D]. */
 VB_API int vb_op_layernorm(int32_t precision, const float* x, const float* gamma, const float* beta, float* out,
                     int32_t M, int32_t D, int32_t iters, float* elapsed_ms);
+
+/* PatchMerger.call (vit_with_patch_merger.py:49-55): x [B,n,D] -> LayerNorm -> softmax(queries [nt,D] . x^T * D^-0.5) . x
+ * -> out [B,nt,D]. */
+VB_API int vb_op_patch_merger(int32_t precision, const float* x, const float* gamma, const float* beta, const float* queries,
+                       float* out, int32_t B, int32_t n, int32_t D, int32_t nt, int32_t iters, float* elapsed_ms);
 
 #ifdef __cplusplus
 }

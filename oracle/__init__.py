@@ -16,5 +16,5 @@ ground truth for the patch ``Rearrange``, and (3) ``tools/ref_tf_dump.py``, a ho
 that dumps golden vectors from the real reference wherever TensorFlow exists.
 """
 from .weights import (make_config, weight_specs, init_weights, stress_weights,  # noqa: F401
-                      make_image, flops_per_image)
+                      make_image, flops_per_image, t2t_token_grid)
 from .spec_numpy import forward as forward_numpy  # noqa: F401

@@ -188,6 +188,67 @@ def _forward_crossvit(img, w, cfg):
             + _linear(_ln(lg[:, 0], w, "lg_head_norm"), w, "lg_head"))
 
 
+def _patch_merger(x, w, pre="patch_merger."):
+    # vit_with_patch_merger.py:49-55
+    x = _ln(x, w, pre + "norm")
+    sim = torch.matmul(w[pre + "queries"], x.transpose(1, 2) * x.shape[-1] ** -0.5)
+    return torch.matmul(torch.softmax(sim, dim=-1), x)
+
+
+def _forward_patch_merger_vit(img, w, cfg):
+    # vit_with_patch_merger.py:174-185, Transformer.call :118-126
+    x = _linear(_im2col(img, cfg["patch_h"], cfg["patch_w"]), w, "patch")
+    x = x + w["pos_embedding"][:, :x.shape[1]]
+    for L in range(cfg["depth"]):
+        pre = f"layers.{L}."
+        x = _attn_vit(_ln(x, w, pre + "attn_norm"), w, pre, cfg["heads"], cfg["dim_head"], False) + x
+        x = _mlp(_ln(x, w, pre + "ff_norm"), w, pre) + x
+        if L == cfg["patch_merge_layer_index"]:
+            x = _patch_merger(x, w)
+    return _linear(_ln(x.mean(dim=1), w, "head_norm"), w, "head")
+
+
+def _unfold_same(x, k, stride):
+    # tf.image.extract_patches(..., padding='SAME') (t2t.py:43) through F.pad + F.unfold; unfold orders the patch vector
+    # (channel, k_row, k_col), TensorFlow (k_row, k_col, channel) -> permute.  x [b, H, W, C] -> [b, oh*ow, k*k*C]
+    b, H, W, C = x.shape
+    oh, ow = (H + stride - 1) // stride, (W + stride - 1) // stride
+    ph, pw = max((oh - 1) * stride + k - H, 0), max((ow - 1) * stride + k - W, 0)
+    xp = F.pad(x.permute(0, 3, 1, 2), (pw // 2, pw - pw // 2, ph // 2, ph - ph // 2))
+    cols = F.unfold(xp, kernel_size=k, stride=stride)                       # [b, C*k*k, L]
+    L = cols.shape[-1]
+    assert L == oh * ow
+    return cols.reshape(b, C, k, k, L).permute(0, 4, 2, 3, 1).reshape(b, L, k * k * C)
+
+
+def _t2t_tokens(img, w, cfg):
+    # t2t.py:58-74 with RearrangeUnfoldTransformer.call :39-48
+    x = img
+    last = len(cfg["t2t_layers"]) - 1
+    for i, (k, st) in enumerate(cfg["t2t_layers"]):
+        if i > 0:
+            b, n, c = x.shape
+            hh = int(n ** 0.5)
+            x = x.reshape(b, hh, n // hh, c)
+        x = _unfold_same(x, k, st)
+        if i != last:
+            d = x.shape[-1]
+            pre = f"t2t.{i}.layers.0."
+            x = _attn_vit(_ln(x, w, pre + "attn_norm"), w, pre, 1, d, False) + x
+            x = _mlp(_ln(x, w, pre + "ff_norm"), w, pre) + x
+    return _linear(x, w, "patch")
+
+
+def _forward_t2t_vit(img, w, cfg):
+    # t2t.py:96-116
+    x = _t2t_tokens(img, w, cfg)
+    b, n, d = x.shape
+    x = torch.cat([w["cls_token"].expand(b, 1, d), x], dim=1) + w["pos_embedding"][:, :n + 1]
+    x = _transformer_vit(x, w, cfg)
+    x = x.mean(dim=1) if cfg["pool"] == "mean" else x[:, 0]
+    return _linear(_ln(x, w, "head_norm"), w, "head")
+
+
 class TorchReference:
     """Holds the weights as torch tensors once; `__call__(img)` -> logits (numpy float32)."""
 
@@ -206,6 +267,10 @@ class TorchReference:
             y = _forward_cait(x, self.w, self.cfg)
         elif kind == "crossvit":
             y = _forward_crossvit(x, self.w, self.cfg)
+        elif kind == "patch_merger_vit":
+            y = _forward_patch_merger_vit(x, self.w, self.cfg)
+        elif kind == "t2t_vit":
+            y = _forward_t2t_vit(x, self.w, self.cfg)
         else:
             raise ValueError(kind)
         return y.float().numpy()

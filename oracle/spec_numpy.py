@@ -204,6 +204,75 @@ def forward_crossvit(img, w, cfg):
     return sm_logits + lg_logits                                          # :301
 
 
+def patch_merger(x, w, pre="patch_merger."):
+    """PatchMerger.call vit_with_patch_merger.py:49-55: LN -> sim = queries . (x^T * dim^-0.5) -> softmax over the tokens ->
+    attn . x; [b, n, dim] -> [b, num_tokens_out, dim]."""
+    d = x.shape[-1]
+    x = layer_norm(x, w, pre + "norm")                                                      # :50
+    sim = np.einsum('td,bnd->btn', w[pre + "queries"], x * d ** -0.5)                       # :51 (scale :45)
+    return np.einsum('btn,bnd->btd', softmax(sim), x)                                       # :52-53
+
+
+def forward_patch_merger_vit(img, w, cfg):
+    """vit_with_patch_merger.py:174-185 (ViT.call) with Transformer.call :118-126."""
+    x = patch_embed(img, w, "patch", cfg["patch_h"], cfg["patch_w"])                        # :175
+    n = x.shape[1]
+    x = x + w["pos_embedding"][:, :n]                                                       # :178 (no cls token)
+    for L in range(cfg["depth"]):
+        pre = f"layers.{L}."
+        x = attention_vit(layer_norm(x, w, pre + "attn_norm"), w, pre, cfg["heads"], cfg["dim_head"]) + x   # :120
+        x = mlp(layer_norm(x, w, pre + "ff_norm"), w, pre) + x                              # :121
+        if L == cfg["patch_merge_layer_index"]:                                             # :123-124
+            x = patch_merger(x, w)
+    x = x.mean(axis=1)                                                                      # Reduce('b n d -> b d', 'mean') :169
+    return dense(layer_norm(x, w, "head_norm"), w, "head")
+
+
+def extract_patches_same(x, k, stride):
+    """tf.image.extract_patches(x, sizes=[1,k,k,1], strides=[1,s,s,1], rates=[1,1,1,1], padding='SAME') (t2t.py:43).
+    TF semantics (third-party, restated): out = ceil(in / s); total padding max((out-1)*s + k - in, 0) with the smaller
+    half BEFORE; out-of-image taps read 0; the patch vector is ordered (k_row, k_col, channel) with channel fastest.
+    x [b, H, W, C] -> [b, oh, ow, k*k*C]."""
+    b, H, W, C = x.shape
+    oh, ow = -(-H // stride), -(-W // stride)
+    ph, pw = max((oh - 1) * stride + k - H, 0), max((ow - 1) * stride + k - W, 0)
+    xp = np.zeros((b, H + ph, W + pw, C), x.dtype)
+    xp[:, ph // 2:ph // 2 + H, pw // 2:pw // 2 + W] = x
+    out = np.empty((b, oh, ow, k, k, C), x.dtype)
+    for i in range(k):
+        for j in range(k):
+            out[:, :, :, i, j] = xp[:, i:i + (oh - 1) * stride + 1:stride, j:j + (ow - 1) * stride + 1:stride]
+    return out.reshape(b, oh, ow, k * k * C)
+
+
+def t2t_tokens(img, w, cfg):
+    """T2TViT.patch_embedding (t2t.py:58-74): per soft-split layer RearrangeUnfoldTransformer.call (:39-48), then Dense(dim)."""
+    x = img
+    last = len(cfg["t2t_layers"]) - 1
+    for i, (k, st) in enumerate(cfg["t2t_layers"]):
+        if i > 0:                                                                           # :40-41
+            hh = int(math.sqrt(x.shape[1]))
+            x = rearrange(x, 'b (h w) c -> b h w c', h=hh)
+        x = extract_patches_same(x, k, st)                                                  # :43
+        x = rearrange(x, 'b h w c -> b (h w) c')                                            # :44
+        if i != last:                                                                       # :45-46: Transformer(dim, heads=1, depth=1, dim_head=dim, mlp_dim=dim)
+            d = x.shape[-1]
+            sub = dict(kind="vit", depth=1, heads=1, dim_head=d)
+            x = transformer_vit(x, w, sub, prefix=f"t2t.{i}.layers.")
+    return dense(x, w, "patch")                                                             # :73
+
+
+def forward_t2t_vit(img, w, cfg):
+    """t2t.py:96-116."""
+    x = t2t_tokens(img, w, cfg)                                                             # :97
+    b, n, d = x.shape
+    x = np.concatenate([np.broadcast_to(w["cls_token"], (b, 1, d)), x], axis=1)             # :100-101
+    x = x + w["pos_embedding"][:, :n + 1]                                                   # :102
+    x = transformer_vit(x, w, cfg)                                                          # :105
+    x = x.mean(axis=1) if cfg["pool"] == "mean" else x[:, 0]                                # :107-110
+    return dense(layer_norm(x, w, "head_norm"), w, "head")                                  # :112
+
+
 def forward(img, weights, cfg, dtype=np.float64):
     """Logits [b, num_classes] for an NHWC image batch, computed in `dtype`."""
     w = {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}
@@ -215,6 +284,10 @@ def forward(img, weights, cfg, dtype=np.float64):
         return forward_cait(img, w, cfg)
     if kind == "crossvit":
         return forward_crossvit(img, w, cfg)
+    if kind == "patch_merger_vit":
+        return forward_patch_merger_vit(img, w, cfg)
+    if kind == "t2t_vit":
+        return forward_t2t_vit(img, w, cfg)
     raise ValueError(kind)
 
 
@@ -232,6 +305,26 @@ def forward_distill(img, distill_token, weights, cfg, dtype=np.float64):
     x, dist = x[:, :-1], x[:, -1]                                                           # :32
     x = x.mean(axis=1) if cfg["pool"] == "mean" else x[:, 0]                                # :34-37
     return dense(layer_norm(x, w, "head_norm"), w, "head"), dist                            # :39-42
+
+
+def embed_tokens(img, weights, cfg, dtype=np.float64):
+    """Everything `call` does before `self.transformer`: patch embedding, cls token (where the model has one), positions
+    (vit.py:160-166, cait.py:181-184, vit_with_patch_merger.py:175-179, t2t.py:97-103, efficient.py:40-45)."""
+    w = {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}
+    img = np.asarray(img, dtype=dtype)
+    x = t2t_tokens(img, w, cfg) if cfg["kind"] == "t2t_vit" else patch_embed(img, w, "patch", cfg["patch_h"], cfg["patch_w"])
+    b, n, d = x.shape
+    if "cls_token" in w and cfg["kind"] != "cait":
+        x = np.concatenate([np.broadcast_to(w["cls_token"], (b, 1, d)), x], axis=1)
+    return x + w["pos_embedding"][:, :x.shape[1]]
+
+
+def head_logits(x, weights, cfg, dtype=np.float64):
+    """Everything `call` does after `self.transformer`: pooling + mlp_head (vit.py:170-175)."""
+    w = {k: np.asarray(v, dtype=dtype) for k, v in weights.items()}
+    x = np.asarray(x, dtype=dtype)
+    x = x.mean(axis=1) if cfg.get("pool", "cls") == "mean" else x[:, 0]
+    return dense(layer_norm(x, w, "head_norm"), w, "head")
 
 
 def transformer_tokens(x, weights, cfg, dtype=np.float64):

@@ -7,6 +7,8 @@ TEST INFRASTRUCTURE (see oracle/__init__.py).  Follows the reference constructor
   CrossViT vit_tensorflow/cross_vit.py:232-288 (+ ImageEmbedder :199-217,
            Transformer :95-107, ProjectInOut :118-126, CrossTransformer :141-150)
   parallel ViT  vit_tensorflow/parallel_vit.py:120-165 (+ Parallel :36-42, Transformer :99-117)
+  patch-merger ViT  vit_tensorflow/vit_with_patch_merger.py:134-172 (+ PatchMerger :42-47, Transformer :104-115)
+  T2TViT   vit_tensorflow/t2t.py:50-94 (+ RearrangeUnfoldTransformer :17-36)
 
 Weight layouts are the Keras layouts: Dense kernel ``[in, out]``, bias ``[out]``,
 LayerNormalization gamma/beta ``[dim]``.
@@ -51,9 +53,45 @@ def make_config(kind: str, **kw) -> dict:
         for p in (cfg["sm_patch_size"], cfg["lg_patch_size"]):
             assert s % p == 0, 'Image dimensions must be divisible by the patch size.'
         cfg.update(image_h=s, image_w=s)
+    elif kind == "patch_merger_vit":
+        # vit_with_patch_merger.py:134-146 (ViT) and :104-109 (Transformer): no cls token, mean pooling in mlp_head (:168-172)
+        cfg = dict(kind=kind, dim_head=64, channels=3, patch_merge_layer=None, patch_merge_num_tokens=8)
+        cfg.update(kw)
+        ih, iw = _pair(cfg["image_size"])
+        ph, pw = _pair(cfg["patch_size"])
+        assert ih % ph == 0 and iw % pw == 0, 'Image dimensions must be divisible by the patch size.'
+        pml = cfg["patch_merge_layer"]
+        cfg.update(image_h=ih, image_w=iw, patch_h=ph, patch_w=pw, num_patches=(ih // ph) * (iw // pw), pool="mean",
+                   patch_merge_layer_index=(pml if pml is not None else cfg["depth"] // 2) - 1)   # :108
+    elif kind == "t2t_vit":
+        # t2t.py:50-94
+        cfg = dict(kind=kind, pool="cls", channels=3, dim_head=64, t2t_layers=((7, 4), (3, 2), (3, 2)))
+        cfg.update(kw)
+        assert cfg["pool"] in {"cls", "mean"}, 'pool type must be either cls (cls token) or mean (mean pooling)'
+        assert all(cfg.get(k) is not None for k in ("depth", "heads", "mlp_dim")), 'depth, heads, and mlp_dim must be supplied'
+        cfg["t2t_layers"] = tuple((int(k), int(s)) for k, s in cfg["t2t_layers"])
+        s = cfg["image_size"]
+        out, layer_dim, dims = s, cfg["channels"], []
+        for k, st in cfg["t2t_layers"]:
+            layer_dim *= k * k                                            # t2t.py:63
+            out = int(((out - k + 2 * (st // 2)) / st) + 1)               # conv_output_size t2t.py:14-15,66
+            dims.append(layer_dim)
+        cfg.update(image_h=s, image_w=s, t2t_dims=tuple(dims), num_patches=out * out)
     else:
         raise ValueError(f"unknown model kind {kind!r}")
     return cfg
+
+
+def t2t_token_grid(cfg, h=None, w=None):
+    """Token grid after every soft-split of T2T: tf.image.extract_patches(..., padding='SAME') yields ceil(size / stride)
+    positions per axis (t2t.py:43); the last entry is the grid the main transformer sees."""
+    h = cfg["image_h"] if h is None else h
+    w = cfg["image_w"] if w is None else w
+    grids = []
+    for _, st in cfg["t2t_layers"]:
+        h, w = -(-h // st), -(-w // st)
+        grids.append((h, w))
+    return grids
 
 
 # ----------------------------------------------------------------------------- specs
@@ -135,6 +173,31 @@ def weight_specs(cfg: dict) -> "collections.OrderedDict[str, tuple]":
                 specs[pre + "attn_scale"] = ((1, 1, dim), ("fill", _layerscale_eps(L + 1)))
                 specs[pre + "ff_scale"] = ((1, 1, dim), ("fill", _layerscale_eps(L + 1)))
                 _vit_layer(specs, pre, dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], kind="cait")
+        _ln(specs, "head_norm", dim)
+        _dense(specs, "head", dim, cfg["num_classes"])
+    elif kind == "patch_merger_vit":
+        dim = cfg["dim"]
+        pd = cfg["patch_h"] * cfg["patch_w"] * C
+        specs["pos_embedding"] = ((1, cfg["num_patches"] + 1, dim), "normal")   # vit_with_patch_merger.py:163 (only [:n] is used, :178)
+        _dense(specs, "patch", pd, dim)
+        for L in range(cfg["depth"]):
+            _vit_layer(specs, f"layers.{L}.", dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], kind="vit")
+        _ln(specs, "patch_merger.norm", dim)                                       # :46
+        specs["patch_merger.queries"] = ((cfg["patch_merge_num_tokens"], dim), "normal")   # :47
+        _ln(specs, "head_norm", dim)
+        _dense(specs, "head", dim, cfg["num_classes"])
+    elif kind == "t2t_vit":
+        dim = cfg["dim"]
+        dims = cfg["t2t_dims"]
+        for i, d in enumerate(dims[:-1]):
+            # RearrangeUnfoldTransformer's Transformer(dim=d, heads=1, depth=1, dim_head=d, mlp_dim=d) (t2t.py:69-70,35):
+            # heads == 1 and dim_head == dim -> no out-projection (vit.py:53)
+            _vit_layer(specs, f"t2t.{i}.layers.0.", d, 1, d, d, kind="vit")
+        _dense(specs, "patch", dims[-1], dim)                                      # t2t.py:73
+        specs["pos_embedding"] = ((1, cfg["num_patches"] + 1, dim), "normal")      # :76
+        specs["cls_token"] = ((1, 1, dim), "normal")                               # :77
+        for L in range(cfg["depth"]):
+            _vit_layer(specs, f"layers.{L}.", dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], kind="vit")
         _ln(specs, "head_norm", dim)
         _dense(specs, "head", dim, cfg["num_classes"])
     elif kind == "crossvit":
@@ -246,6 +309,29 @@ def flops_per_image(cfg: dict) -> float:
         f = 2 * n_p * cfg["patch_h"] * cfg["patch_w"] * C * dim
         f += cfg["depth"] * _layer_flops(n_p, n_p, dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], mixes=2)
         f += cfg["cls_depth"] * _layer_flops(1, n_p + 1, dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], mixes=2)
+        f += 2 * dim * cfg["num_classes"]
+        return float(f)
+    if kind == "patch_merger_vit":
+        n, dim = cfg["num_patches"], cfg["dim"]
+        f = 2 * n * cfg["patch_h"] * cfg["patch_w"] * C * dim
+        po = not (cfg["heads"] == 1 and cfg["dim_head"] == dim)
+        for L in range(cfg["depth"]):
+            f += _layer_flops(n, n, dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], project_out=po)
+            if L == cfg["patch_merge_layer_index"]:
+                f += 4 * cfg["patch_merge_num_tokens"] * n * dim               # queries . x^T and attn . x
+                n = cfg["patch_merge_num_tokens"]
+        f += 2 * dim * cfg["num_classes"]
+        return float(f)
+    if kind == "t2t_vit":
+        f = 0
+        grids = t2t_token_grid(cfg)
+        for i, d in enumerate(cfg["t2t_dims"][:-1]):
+            n = grids[i][0] * grids[i][1]
+            f += _layer_flops(n, n, d, 1, d, d, project_out=False)
+        n_p, dim = grids[-1][0] * grids[-1][1], cfg["dim"]
+        f += 2 * n_p * cfg["t2t_dims"][-1] * dim
+        po = not (cfg["heads"] == 1 and cfg["dim_head"] == dim)
+        f += cfg["depth"] * _layer_flops(n_p + 1, n_p + 1, dim, cfg["heads"], cfg["dim_head"], cfg["mlp_dim"], project_out=po)
         f += 2 * dim * cfg["num_classes"]
         return float(f)
     if kind == "crossvit":

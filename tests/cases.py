@@ -23,6 +23,14 @@ SMALL = {
                            dim_head=16),
     "parallel_three_noproj": dict(kind="parallel_vit", image_size=32, patch_size=8, num_classes=5, dim=64, depth=2, heads=1,
                                   mlp_dim=64, dim_head=64, num_parallel_branches=3, pool="mean"),
+    "merger_small": dict(kind="patch_merger_vit", image_size=64, patch_size=8, num_classes=10, dim=64, depth=4, heads=4, mlp_dim=128,
+                         dim_head=16, patch_merge_layer=2, patch_merge_num_tokens=5),
+    "merger_default_noproj": dict(kind="patch_merger_vit", image_size=(32, 48), patch_size=8, num_classes=6, dim=64, depth=2, heads=1,
+                                  mlp_dim=96, dim_head=64),
+    "t2t_small": dict(kind="t2t_vit", image_size=32, num_classes=10, dim=64, depth=2, heads=4, mlp_dim=128, dim_head=16,
+                      t2t_layers=((3, 2), (3, 2))),
+    "t2t_default_layers": dict(kind="t2t_vit", image_size=64, num_classes=7, dim=64, depth=1, heads=2, mlp_dim=64, dim_head=32,
+                               pool="mean"),
     "crossvit_samedim": dict(kind="crossvit", image_size=32, num_classes=6, sm_dim=64, lg_dim=64, sm_patch_size=8,
                              lg_patch_size=16, sm_enc_depth=1, lg_enc_depth=1, sm_enc_heads=2, lg_enc_heads=2,
                              sm_enc_mlp_dim=64, lg_enc_mlp_dim=64, sm_enc_dim_head=32, lg_enc_dim_head=32,
@@ -34,6 +42,9 @@ MID = {
     "vit_mid": dict(kind="vit", image_size=224, patch_size=16, num_classes=1000, dim=256, depth=2, heads=4, mlp_dim=512),
     "parallel_mid": dict(kind="parallel_vit", image_size=224, patch_size=16, num_classes=100, dim=256, depth=2, heads=4, mlp_dim=512),
     "deepvit_mid": dict(kind="deepvit", image_size=224, patch_size=16, num_classes=100, dim=256, depth=2, heads=4, mlp_dim=512),
+    "merger_mid": dict(kind="patch_merger_vit", image_size=224, patch_size=16, num_classes=100, dim=256, depth=4, heads=4, mlp_dim=512,
+                       patch_merge_layer=2),
+    "t2t_mid": dict(kind="t2t_vit", image_size=224, num_classes=100, dim=256, depth=2, heads=4, mlp_dim=512),
     "cait_mid": dict(kind="cait", image_size=224, patch_size=16, num_classes=100, dim=192, depth=2, cls_depth=2, heads=4,
                      mlp_dim=384, dim_head=48),
 }

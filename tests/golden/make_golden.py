@@ -22,9 +22,12 @@ for name, d in SMALL.items():
     for wname in ("init_weights", "stress_weights"):
         kw = dict(d)
         cfg = oracle.make_config(kw.pop("kind"), **kw)
+        path = os.path.join(HERE, f"{name}__{wname}.npz")
+        if os.path.exists(path) and "--force" not in sys.argv:   # committed fixtures are never rewritten silently
+            continue
         meta = dict(config=d, weights=wname, weight_seed=11, image_seed=12, batch=2)
         w = getattr(oracle, wname)(cfg, 11)
         img = oracle.make_image(cfg, 2, 12)
         logits = oracle.forward_numpy(img, w, cfg)
-        np.savez(os.path.join(HERE, f"{name}__{wname}.npz"), meta=json.dumps(meta), logits_f64=logits)
+        np.savez(path, meta=json.dumps(meta), logits_f64=logits)
         print(name, wname, logits.shape, float(np.abs(logits).mean()))

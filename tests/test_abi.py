@@ -23,7 +23,7 @@ def test_header_symbols_are_exported_and_bound(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/vitb200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES must cover exactly the declared ABI"
-    assert lib.vb_abi_version() == 2
+    assert lib.vb_abi_version() == 3
 
 
 def test_config_struct_layout_matches_header():

@@ -120,6 +120,107 @@ def test_distillable_vit_forward(lib, precision, pool):
     assert (np.abs(plain - refp) <= tol).all()
 
 
+@pytest.mark.parametrize("name", ["vit_small", "vit_mean_rect", "cait_small", "merger_small", "t2t_small"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stage_entries_embed_and_head(lib, name, precision):
+    """vb_forward_embed / vb_forward_head: `call` before and after `self.transformer` (vit.py:160-166,170-175), the two stages the
+    injected-transformer shell (efficient.py) and the wrappers' attribute surface are made of."""
+    from oracle import spec_numpy
+    cfg = cfg_of(name)
+    w = oracle.stress_weights(cfg, 21)
+    img = oracle.make_image(cfg, 3, 22)
+    m = _model(cfg, precision)
+    m.set_weights_dict(w)
+    tol = (lambda r: 1e-4 + 1e-3 * np.abs(r)) if precision == "fp32" else (lambda r: BF16_ATOL + BF16_RTOL * np.abs(r))
+    tok = m.forward_embed(img)
+    ref_tok = spec_numpy.embed_tokens(img, w, cfg)
+    assert tok.shape == ref_tok.shape
+    assert (np.abs(tok - ref_tok) <= tol(ref_tok)).all()
+    x = np.random.default_rng(5).standard_normal((3, 6, cfg["dim"])).astype(np.float32)
+    got = m.forward_head(x)
+    ref = spec_numpy.head_logits(x, w, cfg)
+    assert (np.abs(got - ref) <= tol(ref)).all()
+    np.testing.assert_array_equal(m.mlp_head(x[:, 0]), m.forward_head(x[:, :1]))   # model.mlp_head(x [b, dim])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_patch_embedding_layers(lib, precision):
+    """`patch_embedding.layers[:2]` = (Rearrange, Dense) as mae.py:37 / simmim.py:79 take them apart; `.layers[-1]` mpp.py:200."""
+    from einops import rearrange
+    cfg = cfg_of("vit_mean_rect")
+    w = oracle.stress_weights(cfg, 2)
+    img = oracle.make_image(cfg, 2, 3)
+    m = _model(cfg, precision)
+    m.set_weights_dict(w)
+    to_patch, patch_to_emb = m.patch_embedding.layers[:2]
+    patches = to_patch(img)
+    np.testing.assert_array_equal(patches, rearrange(img, 'b (h p1) (w p2) c -> b (h w) (p1 p2 c)', p1=cfg["patch_h"], p2=cfg["patch_w"]))
+    emb = patch_to_emb(patches)
+    ref = patches.astype(np.float64) @ w["patch.kernel"].astype(np.float64) + w["patch.bias"]
+    tol = (1e-4 + 1e-3 * np.abs(ref)) if precision == "fp32" else (BF16_ATOL + BF16_RTOL * np.abs(ref))
+    assert emb.shape == ref.shape and (np.abs(emb - ref) <= tol).all()
+    np.testing.assert_array_equal(m.patch_embedding(img), emb)
+    assert m.pos_embedding.shape == (1, cfg["num_patches"] + 1, cfg["dim"]) and m.cls_token.shape == (1, 1, cfg["dim"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_efficient_vit_shell(lib, precision):
+    """efficient.ViT (efficient.py:12-55): embed -> injected transformer -> head.  With another engine model's `.transformer`
+    injected and the same weights it must reproduce the plain ViT; with a Python callable the oracle composition."""
+    from oracle import spec_numpy
+    from vit_tensorflow_b200 import EfficientViT, ViT
+    cfg = cfg_of("vit_small")
+    w = oracle.stress_weights(cfg, 9)
+    img = oracle.make_image(cfg, 3, 10)
+    kw = dict(image_size=cfg["image_size"], patch_size=cfg["patch_size"], num_classes=cfg["num_classes"], dim=cfg["dim"])
+    vit = ViT(depth=cfg["depth"], heads=cfg["heads"], mlp_dim=cfg["mlp_dim"], dim_head=cfg["dim_head"], precision=precision, **kw)
+    vit.set_weights_dict(w)
+    shell_w = {k: v for k, v in w.items() if not k.startswith("layers.")}
+    eff = EfficientViT(transformer=vit.transformer, precision=precision, **kw)
+    assert sorted(eff.weight_specs()) == sorted(shell_w)
+    eff.set_weights_dict(shell_w)
+    got = eff(img)
+    ref = oracle.forward_numpy(img, w, cfg)
+    tol = (1e-4 + 1e-3 * np.abs(ref)) if precision == "fp32" else (BF16_ATOL + BF16_RTOL * np.abs(ref))
+    assert (np.abs(got - ref) <= tol).all()
+    # an arbitrary callable: tokens -> 0.5 * tokens reversed along n
+    eff2 = EfficientViT(transformer=lambda x, training=True: 0.5 * x[:, ::-1], pool="mean", precision=precision, **kw)
+    eff2.set_weights_dict(shell_w)
+    cfg2 = dict(cfg, pool="mean")
+    ref2 = spec_numpy.head_logits(0.5 * spec_numpy.embed_tokens(img, w, cfg2)[:, ::-1], w, cfg2)
+    got2 = eff2(img)
+    tol2 = (1e-4 + 1e-3 * np.abs(ref2)) if precision == "fp32" else (BF16_ATOL + BF16_RTOL * np.abs(ref2))
+    assert (np.abs(got2 - ref2) <= tol2).all()
+
+
+def test_t2t_injected_transformer_and_smaller_image(lib):
+    """T2TViT(transformer=...) (t2t.py:82-86) and a smaller image than configured (pos_embedding[:, :n+1], t2t.py:102)."""
+    from oracle import spec_numpy
+    from vit_tensorflow_b200 import T2TViT
+    cfg = cfg_of("t2t_small")
+    w = oracle.stress_weights(cfg, 13)
+    m = _model(cfg, "fp32")
+    m.set_weights_dict(w)
+    img = oracle.make_image(cfg, 2, 14, h=24, w=24)
+    np.testing.assert_allclose(m(img), oracle.forward_numpy(img, w, cfg), rtol=1e-3, atol=1e-4)
+    inj = T2TViT(image_size=cfg["image_size"], num_classes=cfg["num_classes"], dim=cfg["dim"], t2t_layers=cfg["t2t_layers"],
+                 transformer=m.transformer, precision="fp32")
+    inj.set_weights_dict({k: v for k, v in w.items() if not k.startswith("layers.")})
+    img = oracle.make_image(cfg, 2, 15)
+    np.testing.assert_allclose(inj(img), oracle.forward_numpy(img, w, cfg), rtol=1e-3, atol=1e-4)
+
+
+def test_patch_merger_never_merges_when_index_out_of_range(lib):
+    # depth = 1 -> default(patch_merge_layer, depth // 2) - 1 = -1: the merger is never applied (vit_with_patch_merger.py:108,123)
+    cfg = oracle.make_config("patch_merger_vit", image_size=32, patch_size=8, num_classes=4, dim=64, depth=1, heads=2, mlp_dim=64, dim_head=32)
+    assert cfg["patch_merge_layer_index"] == -1
+    w = oracle.stress_weights(cfg, 1)
+    img = oracle.make_image(cfg, 2, 2)
+    m = _model(cfg, "fp32")
+    m.set_weights_dict(w)
+    np.testing.assert_allclose(m(img), oracle.forward_numpy(img, w, cfg), rtol=1e-3, atol=1e-4)
+
+
 def test_batch_independence_and_determinism(lib):
     """Images are independent (no cross-sample op): logits of a batch equal logits of its halves, bit for bit,
     and repeated calls are bit-identical (what the data-parallel sharding relies on)."""

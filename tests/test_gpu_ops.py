@@ -140,3 +140,27 @@ def test_attention(lib, precision, variant, B, nq, nk, heads, dh):
     else:
         # P is rounded to bf16 before the PV product on the tensor-core path: 2^-8 relative per probability
         np.testing.assert_allclose(out, ref, rtol=2e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 49, 64, 5), (3, 196, 256, 8), (1, 10, 24, 3)])
+def test_patch_merger_op(lib, precision, shape):
+    """PatchMerger.call (vit_with_patch_merger.py:49-55) against the float64 spec."""
+    from oracle import spec_numpy
+    from vit_tensorflow_b200 import _lib
+    B, n, D, nt = shape
+    rng = np.random.default_rng(B * 1000 + n)
+    x = rng.standard_normal((B, n, D)).astype(np.float32)
+    w = {"patch_merger.norm.gamma": (1 + 0.2 * rng.standard_normal(D)).astype(np.float32),
+         "patch_merger.norm.beta": (0.2 * rng.standard_normal(D)).astype(np.float32),
+         "patch_merger.queries": rng.standard_normal((nt, D)).astype(np.float32)}
+    if precision == "bf16":
+        from cases import bf16_round
+        x = bf16_round(x)
+    got, _ = _lib.op_patch_merger(x, w["patch_merger.norm.gamma"], w["patch_merger.norm.beta"], w["patch_merger.queries"], precision=precision)
+    ref = spec_numpy.patch_merger(x.astype(np.float64), {k: v.astype(np.float64) for k, v in w.items()})
+    assert got.shape == (B, nt, D)
+    if precision == "fp32":
+        np.testing.assert_allclose(got, ref, rtol=1e-3, atol=1e-4)
+    else:
+        assert (np.abs(got - ref) <= 3e-2 + 3e-2 * np.abs(ref)).all()

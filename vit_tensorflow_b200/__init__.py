@@ -7,6 +7,8 @@ hand-written sm_100a CUDA in `libvitb200.so` (sources under `csrc/`, C-ABI in `i
 Importing the package does not load the library; constructing a model does, and fails loudly when the library
 or a B200 is missing -- there is no CPU / PyTorch fallback.
 """
-from .models import ViT, DeepViT, CaiT, CrossViT, DistillableViT, ParallelViT, from_config, pair  # noqa: F401
+from .models import (ViT, DeepViT, CaiT, CrossViT, DistillableViT, ParallelViT, T2TViT, PatchMergerViT, PatchMerger,  # noqa: F401
+                     EfficientViT, from_config, pair)
 
-__all__ = ["ViT", "DeepViT", "CaiT", "CrossViT", "DistillableViT", "ParallelViT", "from_config"]
+__all__ = ["ViT", "DeepViT", "CaiT", "CrossViT", "DistillableViT", "ParallelViT", "T2TViT", "PatchMergerViT", "PatchMerger",
+           "EfficientViT", "from_config"]

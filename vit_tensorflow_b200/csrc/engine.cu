@@ -175,7 +175,20 @@ struct vb_handle {
 
   // model structure (filled by finalize)
   EmbedW embed, sm_embed, lg_embed;
-  std::vector<LayerW> layers, cls_layers;
+  std::vector<LayerW> layers, cls_layers, t2t_layers;   // t2t_layers: the one-layer transformers between the soft splits (t2t.py:35)
+  Norm merger_norm;                                     // PatchMerger (vit_with_patch_merger.py:46-47)
+  const float* merger_queries = nullptr;
+  struct T2TStage { int k, stride, dim; };              // dim = channels * prod(k^2) up to and including this stage (t2t.py:63)
+  std::vector<T2TStage> t2t_stages() const {
+    const int ks[4] = {cfg.t2t_k0, cfg.t2t_k1, cfg.t2t_k2, cfg.t2t_k3}, ss[4] = {cfg.t2t_s0, cfg.t2t_s1, cfg.t2t_s2, cfg.t2t_s3};
+    std::vector<T2TStage> st;
+    int d = cfg.channels;
+    for (int i = 0; i < cfg.t2t_num_layers; ++i) { d *= ks[i] * ks[i]; st.push_back(T2TStage{ks[i], ss[i], d}); }
+    return st;
+  }
+  static int conv_output_size(int size, int k, int stride) {   // t2t.py:14-15 with padding = stride // 2
+    return static_cast<int>((static_cast<double>(size - k + 2 * (stride / 2)) / stride) + 1);
+  }
   struct XBlock { std::vector<LayerW> sm_layers, lg_layers; Norm sm_final, lg_final; std::vector<CrossW> sm_attend_lg, lg_attend_sm; };
   std::vector<XBlock> xblocks;
   Norm head_norm, sm_head_norm, lg_head_norm;
@@ -235,6 +248,29 @@ struct vb_handle {
           expect_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind);
         }
       }
+      expect_ln("head_norm", c.dim);
+      expect_dense("head", c.dim, c.num_classes);
+    } else if (c.kind == VB_KIND_PATCH_MERGER_VIT) {
+      const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
+      expect("pos_embedding", {1, np + 1, c.dim});                       // vit_with_patch_merger.py:163
+      expect_dense("patch", c.patch_h * c.patch_w * C, c.dim);
+      for (int L = 0; L < c.depth; ++L) expect_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_VIT);
+      expect_ln("patch_merger.norm", c.dim);
+      expect("patch_merger.queries", {c.patch_merge_num_tokens, c.dim});
+      expect_ln("head_norm", c.dim);
+      expect_dense("head", c.dim, c.num_classes);
+    } else if (c.kind == VB_KIND_T2T_VIT) {
+      const auto st = t2t_stages();
+      int out = c.image_h;
+      for (size_t i = 0; i < st.size(); ++i) {
+        out = conv_output_size(out, st[i].k, st[i].stride);             // t2t.py:66
+        if (i + 1 < st.size())                                           // Transformer(dim=d, heads=1, depth=1, dim_head=d, mlp_dim=d) t2t.py:69-70
+          expect_layer("t2t." + std::to_string(i) + ".layers.0.", st[i].dim, 1, st[i].dim, st[i].dim, VB_KIND_VIT);
+      }
+      expect_dense("patch", st.back().dim, c.dim);                        // t2t.py:73
+      expect("pos_embedding", {1, out * out + 1, c.dim});                 // :76
+      expect("cls_token", {1, 1, c.dim});
+      for (int L = 0; L < c.depth; ++L) expect_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_VIT);
       expect_ln("head_norm", c.dim);
       expect_dense("head", c.dim, c.num_classes);
     } else if (c.kind == VB_KIND_CAIT) {
@@ -375,9 +411,9 @@ struct vb_handle {
     l.fc2 = make_linear(pre + "fc2", mlp, dim);
     return l;
   }
-  EmbedW make_embed(const std::string& pre, int p_h, int p_w, int dim, int n_pos, bool with_cls = true) {
+  EmbedW make_embed(const std::string& pre, int p_h, int p_w, int dim, int n_pos, bool with_cls = true, int K = 0) {
     EmbedW e;
-    e.patch = make_linear(pre + "patch", p_h * p_w * cfg.channels, dim);
+    e.patch = make_linear(pre + "patch", K > 0 ? K : p_h * p_w * cfg.channels, dim);
     e.pos = W(pre + "pos_embedding");
     e.cls = with_cls ? W(pre + "cls_token") : nullptr;   // CaiT adds its cls token after the patch stage (cait.py:189)
     e.dim = dim; e.n_pos = n_pos;
@@ -387,7 +423,7 @@ struct vb_handle {
   void finalize() {
     for (auto& w : weights) VB_CHECK(w.set, "vb_finalize: weight '" + w.name + "' was never set");
     VB_CUDA(cudaSetDevice(device));
-    owned.clear(); layers.clear(); cls_layers.clear(); xblocks.clear(); plans.clear(); embed_res.clear();
+    owned.clear(); layers.clear(); cls_layers.clear(); t2t_layers.clear(); xblocks.clear(); plans.clear(); embed_res.clear();
     const vb_config& c = cfg;
     if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT || c.kind == VB_KIND_PARALLEL_VIT) {
       const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
@@ -400,6 +436,26 @@ struct vb_handle {
           layers.push_back(make_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, c.kind));
         }
       }
+      head_norm = make_norm("head_norm", c.dim);
+      head = make_linear_f32("head", c.dim, c.num_classes);
+    } else if (c.kind == VB_KIND_PATCH_MERGER_VIT) {
+      const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
+      embed = make_embed("", c.patch_h, c.patch_w, c.dim, np + 1, false);
+      for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_VIT));
+      merger_norm = make_norm("patch_merger.norm", c.dim);
+      merger_queries = W("patch_merger.queries");
+      head_norm = make_norm("head_norm", c.dim);
+      head = make_linear_f32("head", c.dim, c.num_classes);
+    } else if (c.kind == VB_KIND_T2T_VIT) {
+      const auto st = t2t_stages();
+      int out = c.image_h;
+      for (size_t i = 0; i < st.size(); ++i) {
+        out = conv_output_size(out, st[i].k, st[i].stride);
+        if (i + 1 < st.size())
+          t2t_layers.push_back(make_layer("t2t." + std::to_string(i) + ".layers.0.", st[i].dim, 1, st[i].dim, st[i].dim, VB_KIND_VIT, false));
+      }
+      embed = make_embed("", 0, 0, c.dim, out * out + 1, true, st.back().dim);
+      for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_VIT));
       head_norm = make_norm("head_norm", c.dim);
       head = make_linear_f32("head", c.dim, c.num_classes);
     } else if (c.kind == VB_KIND_CAIT) {
@@ -494,6 +550,14 @@ struct vb_handle {
       ProfScope ps(this, PROF_EMBED, 0.0, 4.0 * B * H * Wd * cfg.channels + static_cast<double>(sizeof(T)) * M * Kp, s);
       im2col<T>(img, col, B, H, Wd, cfg.channels, ph, pw, has_cls, Kp, s);
     }
+    *rows_out = rows;
+    return embed_from_cols<T>(e, col, Kp, B, rows, s, stats_out);
+  }
+  // X = cols . W + bias + (pos (+ cls on row 0)): the Dense of the patch embedding with cls concat and positions folded
+  // into its residual operand.  cols [B*rows, Kp]: patch vectors, zero in the cls rows and in the pad columns.
+  template <typename T>
+  T* embed_from_cols(const EmbedW& e, const T* col, int Kp, int B, int rows, cudaStream_t s, float** stats_out) {
+    const int M = B * rows;
     const T* R = embed_residual<T>(e, B, rows, s);
     T* X = arena.get<T>(static_cast<size_t>(M) * e.dim);
     Epi ep; ep.bias = e.patch.bias; ep.res = R; ep.ldr = e.dim;
@@ -504,8 +568,61 @@ struct vb_handle {
     Linear L = e.patch;
     L.K = Kp;  // im2col zero-pads the patch vector to the packed weight pitch
     linear<T>(col, Kp, M, L, X, e.dim, ep, s);
-    *rows_out = rows;
     return X;
+  }
+
+  // T2TViT.patch_embedding + cls + positions (t2t.py:58-74,97-103): soft split i = unfold_same over the previous token map
+  // (the image for i = 0), every split but the last followed by a one-layer transformer of width channels * prod(k^2);
+  // the last split writes the im2col operand of the Dense(dim) directly (cls rows / pad columns zero).
+  template <typename T>
+  T* embed_t2t(const float* img, int B, int H, int Wd, int* rows_out, cudaStream_t s, float** stats_out) {
+    const auto st = t2t_stages();
+    const T* map = nullptr;
+    int mh = H, mw = Wd, mc = cfg.channels;
+    for (size_t i = 0; i < st.size(); ++i) {
+      const int oh = (mh + st[i].stride - 1) / st[i].stride, ow = (mw + st[i].stride - 1) / st[i].stride;
+      const int D = st[i].dim, n = oh * ow;
+      VB_CHECK(i == 0 || mh == mw, "T2TViT: token maps after the first soft split must be square (t2t.py:41)");
+      const bool last = i + 1 == st.size();
+      const int ld = last ? (bf16() ? embed.patch.ldw : embed.patch.K) : D;
+      const int cls_row = last ? 1 : 0;
+      T* out = arena.get<T>(static_cast<size_t>(B) * (n + cls_row) * ld);
+      {
+        ProfScope ps(this, PROF_EMBED, 0.0, static_cast<double>(i == 0 ? 4 : sizeof(T)) * B * mh * mw * mc + static_cast<double>(sizeof(T)) * B * (n + cls_row) * ld, s);
+        if (i == 0) unfold_same<float, T>(img, out, B, mh, mw, mc, st[i].k, st[i].stride, cls_row, ld, s);
+        else unfold_same<T, T>(map, out, B, mh, mw, mc, st[i].k, st[i].stride, cls_row, ld, s);
+      }
+      if (last) {
+        VB_CHECK(n + 1 <= embed.n_pos, "image has more patches than pos_embedding rows");
+        *rows_out = n + 1;
+        return embed_from_cols<T>(embed, out, ld, B, n + 1, s, stats_out);
+      }
+      layer_self<T>(out, B, n, D, t2t_layers[i], s);
+      map = out; mh = oh; mw = ow; mc = D;
+    }
+    VB_CHECK(false, "T2TViT needs at least one t2t layer");
+    return nullptr;
+  }
+
+  // `call` up to the transformer for every kind with one token stream
+  template <typename T>
+  T* embed_any(const float* img, int B, int H, int Wd, int* rows_out, cudaStream_t s, float** stats_out) {
+    VB_CHECK(cfg.kind != VB_KIND_CROSSVIT, "CrossViT has two token streams: no single embedding stage");
+    if (cfg.kind == VB_KIND_T2T_VIT) return embed_t2t<T>(img, B, H, Wd, rows_out, s, stats_out);
+    return embed_tokens<T>(embed, img, B, H, Wd, cfg.patch_h, cfg.patch_w, rows_out, s, stats_out);
+  }
+
+  // PatchMerger.call (vit_with_patch_merger.py:49-55) = single-head attention of nt learned queries over LN(x) with
+  // keys = values = LN(x) and scale dim^-0.5 (:45) -- exactly attention with heads = 1, dim_head = dim.
+  template <typename T>
+  T* patch_merge(const T* X, int B, int rows, int dim, const Norm& norm, const float* queries, int nt, cudaStream_t s) {
+    T* Y = arena.get<T>(static_cast<size_t>(B) * rows * dim);
+    ln<T>(X, norm, Y, B * rows, dim, s);
+    T* Q = arena.get<T>(static_cast<size_t>(B) * nt * dim);
+    broadcast_rows<T>(queries, Q, B, nt, dim, s);
+    T* O = arena.get<T>(static_cast<size_t>(B) * nt * dim);
+    attention_dispatch<T>(Q, dim, Y, dim, Y, dim, O, dim, B, nt, rows, 1, dim, 0, nullptr, nullptr, nullptr, nullptr, s);
+    return O;
   }
 
   // one pre-norm layer, self-attention over all rows (vit.py:101-102, cait.py:150-151, cross_vit.py:109-111).
@@ -686,13 +803,27 @@ struct vb_handle {
   void forward_impl(const float* img, int B, int H, int Wd, float* logits, cudaStream_t s) {
     const vb_config& c = cfg;
     arena.reset();
-    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT) {
+    if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT || c.kind == VB_KIND_T2T_VIT) {
+      int rows = 0;
+      float* stats = nullptr;
+      T* X = embed_any<T>(img, B, H, Wd, &rows, s, &stats);
+      bool sv = stats != nullptr;
+      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s, stats, &sv);
+      classify<T>(X, rows, c.dim, head_norm, head, B, c.pool == VB_POOL_MEAN, logits, false, s);
+    } else if (c.kind == VB_KIND_PATCH_MERGER_VIT) {   // vit_with_patch_merger.py:174-185, Transformer.call :118-126
       int rows = 0;
       float* stats = nullptr;
       T* X = embed_tokens<T>(embed, img, B, H, Wd, c.patch_h, c.patch_w, &rows, s, &stats);
       bool sv = stats != nullptr;
-      for (const auto& l : layers) layer_self<T>(X, B, rows, c.dim, l, s, stats, &sv);
-      classify<T>(X, rows, c.dim, head_norm, head, B, c.pool == VB_POOL_MEAN, logits, false, s);
+      for (int L = 0; L < c.depth; ++L) {
+        layer_self<T>(X, B, rows, c.dim, layers[L], s, stats, &sv);
+        if (L == c.patch_merge_layer_index) {
+          X = patch_merge<T>(X, B, rows, c.dim, merger_norm, merger_queries, c.patch_merge_num_tokens, s);
+          rows = c.patch_merge_num_tokens;
+          sv = false;                                    // new token rows: the row statistics are recomputed by the next layer
+        }
+      }
+      classify<T>(X, rows, c.dim, head_norm, head, B, 1, logits, false, s);   // Reduce('b n d -> b d', 'mean') :169
     } else if (c.kind == VB_KIND_PARALLEL_VIT) {
       int rows = 0;
       float* stats = nullptr;
@@ -775,7 +906,8 @@ struct vb_handle {
 
   template <typename T>
   void tokens_impl(const float* tok, int B, int n, float* out, cudaStream_t s) {
-    VB_CHECK(cfg.kind == VB_KIND_VIT || cfg.kind == VB_KIND_DEEPVIT, "vb_forward_tokens supports ViT / DeepViT");
+    VB_CHECK(cfg.kind == VB_KIND_VIT || cfg.kind == VB_KIND_DEEPVIT || cfg.kind == VB_KIND_T2T_VIT,
+             "vb_forward_tokens supports ViT / DeepViT / T2TViT");
     arena.reset();
     const long long count = static_cast<long long>(B) * n * cfg.dim;
     T* X;
@@ -791,6 +923,55 @@ struct vb_handle {
     for (const auto& l : layers) layer_self<T>(X, B, n, cfg.dim, l, s, stats, &sv);
     if (sizeof(T) == 4) VB_CUDA(cudaMemcpyAsync(out, X, count * 4, cudaMemcpyDeviceToDevice, s));
     else convert<__nv_bfloat16, float>(reinterpret_cast<const __nv_bfloat16*>(X), out, count, s);
+  }
+
+  // ---------------------------------------------------------------- stage entries (vb_forward_embed / _head / vb_patch_to_emb)
+  int embed_rows(int H, int Wd) const {
+    VB_CHECK(cfg.kind != VB_KIND_CROSSVIT, "CrossViT has two token streams: no single embedding stage");
+    if (cfg.kind == VB_KIND_T2T_VIT) {
+      int h = H, w = Wd;
+      for (const auto& st : t2t_stages()) { h = (h + st.stride - 1) / st.stride; w = (w + st.stride - 1) / st.stride; }
+      return h * w + 1;
+    }
+    VB_CHECK(H % cfg.patch_h == 0 && Wd % cfg.patch_w == 0, "Image dimensions must be divisible by the patch size.");
+    const bool has_cls = cfg.kind != VB_KIND_CAIT && cfg.kind != VB_KIND_PATCH_MERGER_VIT;
+    return (H / cfg.patch_h) * (Wd / cfg.patch_w) + (has_cls ? 1 : 0);
+  }
+  template <typename T>
+  void to_f32(const T* X, float* out, long long count, cudaStream_t s) {
+    if (sizeof(T) == 4) VB_CUDA(cudaMemcpyAsync(out, X, count * 4, cudaMemcpyDeviceToDevice, s));
+    else convert<__nv_bfloat16, float>(reinterpret_cast<const __nv_bfloat16*>(X), out, count, s);
+  }
+  template <typename T>
+  void embed_impl(const float* img, int B, int H, int Wd, float* tokens, cudaStream_t s) {
+    arena.reset();
+    int rows = 0;
+    T* X = embed_any<T>(img, B, H, Wd, &rows, s, nullptr);
+    to_f32<T>(X, tokens, static_cast<long long>(B) * rows * cfg.dim, s);
+  }
+  template <typename T>
+  void head_impl(const float* tok, int B, int n, float* logits, cudaStream_t s) {
+    VB_CHECK(cfg.kind != VB_KIND_CROSSVIT, "CrossViT sums two heads: no single mlp_head stage");
+    arena.reset();
+    const long long count = static_cast<long long>(B) * n * cfg.dim;
+    T* X = arena.get<T>(count);
+    convert_rows<float, T>(tok, cfg.dim, X, cfg.dim, static_cast<long long>(B) * n, cfg.dim, s);
+    const bool mean = cfg.kind == VB_KIND_PATCH_MERGER_VIT || (cfg.kind != VB_KIND_CAIT && cfg.pool == VB_POOL_MEAN);
+    classify<T>(X, n, cfg.dim, head_norm, head, B, mean ? 1 : 0, logits, false, s);
+  }
+  template <typename T>
+  void patch_to_emb_impl(const float* patches, int rows, float* out, cudaStream_t s) {
+    VB_CHECK(cfg.kind != VB_KIND_CROSSVIT, "CrossViT has two patch embeddings");
+    arena.reset();
+    const int K = embed.patch.K, Kp = bf16() ? embed.patch.ldw : K;
+    T* col = arena.get<T>(static_cast<size_t>(rows) * Kp);
+    convert_rows<float, T>(patches, K, col, Kp, rows, K, s);
+    T* Y = arena.get<T>(static_cast<size_t>(rows) * cfg.dim);
+    Epi ep; ep.bias = embed.patch.bias;
+    Linear L = embed.patch;
+    L.K = Kp;
+    linear<T>(col, Kp, rows, L, Y, cfg.dim, ep, s);
+    to_f32<T>(Y, out, static_cast<long long>(rows) * cfg.dim, s);
   }
 };
 
@@ -889,7 +1070,7 @@ int guarded(vb_handle* h, F&& f) {
 
 void validate(const vb_config& c) {
   VB_CHECK(c.struct_size == static_cast<int32_t>(sizeof(vb_config)), "vb_config.struct_size mismatch (ABI)");
-  VB_CHECK(c.kind >= VB_KIND_VIT && c.kind <= VB_KIND_PARALLEL_VIT, "unknown model kind");
+  VB_CHECK(c.kind >= VB_KIND_VIT && c.kind <= VB_KIND_T2T_VIT, "unknown model kind");
   VB_CHECK(c.kind != VB_KIND_PARALLEL_VIT || (c.parallel_branches >= 1 && c.parallel_branches <= 8), "num_parallel_branches must be in [1, 8]");
   VB_CHECK(c.precision == VB_PRECISION_FP32 || c.precision == VB_PRECISION_BF16, "unknown precision");
   VB_CHECK(c.channels > 0 && c.num_classes > 0 && c.image_h > 0 && c.image_w > 0, "bad image / class configuration");
@@ -900,8 +1081,21 @@ void validate(const vb_config& c) {
     VB_CHECK(c.sm_dim > 0 && c.lg_dim > 0 && c.cross_depth > 0 && c.cross_attn_depth >= 0, "bad CrossViT dimensions");
     VB_CHECK(c.sm_enc_heads <= 32 && c.lg_enc_heads <= 32 && c.cross_attn_heads <= 32, "at most 32 heads");
   } else {
-    VB_CHECK(c.patch_h > 0 && c.patch_w > 0 && c.image_h % c.patch_h == 0 && c.image_w % c.patch_w == 0,
-             "Image dimensions must be divisible by the patch size.");
+    if (c.kind == VB_KIND_T2T_VIT) {
+      VB_CHECK(c.image_h == c.image_w, "T2TViT takes a square integer image_size");
+      VB_CHECK(c.t2t_num_layers >= 1 && c.t2t_num_layers <= 4, "t2t_layers: between 1 and 4 (kernel_size, stride) pairs");
+      const int ks[4] = {c.t2t_k0, c.t2t_k1, c.t2t_k2, c.t2t_k3}, ss[4] = {c.t2t_s0, c.t2t_s1, c.t2t_s2, c.t2t_s3};
+      long long d = c.channels;
+      for (int i = 0; i < c.t2t_num_layers; ++i) {
+        VB_CHECK(ks[i] > 0 && ss[i] > 0, "t2t_layers: kernel sizes and strides must be positive");
+        d *= static_cast<long long>(ks[i]) * ks[i];
+        VB_CHECK(d <= (1 << 20), "t2t_layers: token width channels * prod(kernel_size^2) is too large");
+      }
+    } else {
+      VB_CHECK(c.patch_h > 0 && c.patch_w > 0 && c.image_h % c.patch_h == 0 && c.image_w % c.patch_w == 0,
+               "Image dimensions must be divisible by the patch size.");
+    }
+    VB_CHECK(c.kind != VB_KIND_PATCH_MERGER_VIT || c.patch_merge_num_tokens > 0, "patch_merge_num_tokens must be positive");
     VB_CHECK(c.dim > 0 && c.depth >= 0 && c.heads > 0 && c.dim_head > 0 && c.mlp_dim > 0, "bad transformer dimensions");
     VB_CHECK(c.heads <= 32, "at most 32 heads");
     VB_CHECK(c.pool == VB_POOL_CLS || c.pool == VB_POOL_MEAN, "pool type must be either cls (cls token) or mean (mean pooling)");
@@ -960,6 +1154,34 @@ void download(const T* dev, float* host, size_t count) {
     tmp.ensure(count * 4);
     convert<__nv_bfloat16, float>(reinterpret_cast<const __nv_bfloat16*>(dev), static_cast<float*>(tmp.p), static_cast<long long>(count), 0);
     VB_CUDA(cudaMemcpy(host, tmp.p, count * 4, cudaMemcpyDeviceToHost));
+  }
+}
+}  // namespace
+
+namespace {
+// Shared plumbing of the stage entries: optional host->device staging of the input, device staging of a host output,
+// launch accounting, and the final copy + synchronise when the output is a host buffer.
+template <typename F>
+void staged_call(vb_handle* h, const float* in, int32_t in_mem, size_t in_bytes, float* out, int32_t out_mem, size_t out_bytes,
+                 cudaStream_t s, F&& body) {
+  VB_CUDA(cudaSetDevice(h->device));
+  const long long before = launch_counter();
+  const float* in_d = in;
+  if (in_mem == VB_MEM_HOST) {
+    h->tokens_in.ensure(in_bytes);
+    VB_CUDA(cudaMemcpyAsync(h->tokens_in.p, in, in_bytes, cudaMemcpyHostToDevice, s));
+    in_d = static_cast<const float*>(h->tokens_in.p);
+  }
+  float* out_d = out;
+  if (out_mem == VB_MEM_HOST) {
+    h->tokens_out.ensure(out_bytes);
+    out_d = static_cast<float*>(h->tokens_out.p);
+  }
+  body(in_d, out_d);
+  h->last_launches = launch_counter() - before;
+  if (out_mem == VB_MEM_HOST) {
+    VB_CUDA(cudaMemcpyAsync(out, out_d, out_bytes, cudaMemcpyDeviceToHost, s));
+    VB_CUDA(cudaStreamSynchronize(s));
   }
 }
 }  // namespace
@@ -1129,6 +1351,82 @@ int vb_forward_tokens(vb_handle* h, const float* tokens, int32_t tokens_mem, int
   });
 }
 
+int vb_embed_rows(vb_handle* h, int32_t img_h, int32_t img_w) {
+  int rows = -1;
+  const int rc = guarded(h, [&] {
+    VB_CHECK(h != nullptr && img_h > 0 && img_w > 0, "vb_embed_rows: bad arguments");
+    rows = h->embed_rows(img_h, img_w);
+  });
+  return rc == 0 ? rows : -rc;
+}
+
+int vb_forward_embed(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w, float* tokens,
+                     int32_t tokens_mem, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && img != nullptr && tokens != nullptr, "vb_forward_embed: null argument");
+    VB_CHECK(h->finalized, "vb_forward_embed: call vb_finalize after setting the weights");
+    VB_CHECK(batch > 0 && img_h > 0 && img_w > 0, "vb_forward_embed: bad batch / image size");
+    const int rows = h->embed_rows(img_h, img_w);
+    const size_t in_bytes = static_cast<size_t>(batch) * img_h * img_w * h->cfg.channels * sizeof(float);
+    const size_t out_bytes = static_cast<size_t>(batch) * rows * h->cfg.dim * sizeof(float);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    staged_call(h, img, img_mem, in_bytes, tokens, tokens_mem, out_bytes, s, [&](const float* in_d, float* out_d) {
+      if (h->bf16()) h->embed_impl<__nv_bfloat16>(in_d, batch, img_h, img_w, out_d, s);
+      else h->embed_impl<float>(in_d, batch, img_h, img_w, out_d, s);
+    });
+  });
+}
+
+int vb_forward_head(vb_handle* h, const float* tokens, int32_t tokens_mem, int32_t batch, int32_t n, float* logits,
+                    int32_t logits_mem, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && tokens != nullptr && logits != nullptr, "vb_forward_head: null argument");
+    VB_CHECK(h->finalized, "vb_forward_head: call vb_finalize after setting the weights");
+    VB_CHECK(batch > 0 && n > 0, "vb_forward_head: bad shape");
+    const size_t in_bytes = static_cast<size_t>(batch) * n * h->cfg.dim * sizeof(float);
+    const size_t out_bytes = static_cast<size_t>(batch) * h->cfg.num_classes * sizeof(float);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    staged_call(h, tokens, tokens_mem, in_bytes, logits, logits_mem, out_bytes, s, [&](const float* in_d, float* out_d) {
+      if (h->bf16()) h->head_impl<__nv_bfloat16>(in_d, batch, n, out_d, s);
+      else h->head_impl<float>(in_d, batch, n, out_d, s);
+    });
+  });
+}
+
+int vb_to_patch(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, int32_t img_h, int32_t img_w, float* patches,
+                int32_t patches_mem, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && img != nullptr && patches != nullptr, "vb_to_patch: null argument");
+    VB_CHECK(h->cfg.kind != VB_KIND_CROSSVIT && h->cfg.kind != VB_KIND_T2T_VIT, "vb_to_patch: the model has no single Rearrange patch layer");
+    VB_CHECK(batch > 0 && img_h > 0 && img_w > 0, "vb_to_patch: bad batch / image size");
+    const vb_config& c = h->cfg;
+    VB_CHECK(img_h % c.patch_h == 0 && img_w % c.patch_w == 0, "Image dimensions must be divisible by the patch size.");
+    const int np = (img_h / c.patch_h) * (img_w / c.patch_w), pd = c.patch_h * c.patch_w * c.channels;
+    const size_t in_bytes = static_cast<size_t>(batch) * img_h * img_w * c.channels * sizeof(float);
+    const size_t out_bytes = static_cast<size_t>(batch) * np * pd * sizeof(float);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    staged_call(h, img, img_mem, in_bytes, patches, patches_mem, out_bytes, s, [&](const float* in_d, float* out_d) {
+      im2col<float>(in_d, out_d, batch, img_h, img_w, c.channels, c.patch_h, c.patch_w, 0, pd, s);
+    });
+  });
+}
+
+int vb_patch_to_emb(vb_handle* h, const float* patches, int32_t patches_mem, int32_t rows, float* out, int32_t out_mem, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && patches != nullptr && out != nullptr, "vb_patch_to_emb: null argument");
+    VB_CHECK(h->finalized, "vb_patch_to_emb: call vb_finalize after setting the weights");
+    VB_CHECK(h->cfg.kind != VB_KIND_CROSSVIT, "vb_patch_to_emb: CrossViT has two patch embeddings");
+    VB_CHECK(rows > 0, "vb_patch_to_emb: bad shape");
+    const size_t in_bytes = static_cast<size_t>(rows) * h->embed.patch.K * sizeof(float);
+    const size_t out_bytes = static_cast<size_t>(rows) * h->cfg.dim * sizeof(float);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    staged_call(h, patches, patches_mem, in_bytes, out, out_mem, out_bytes, s, [&](const float* in_d, float* out_d) {
+      if (h->bf16()) h->patch_to_emb_impl<__nv_bfloat16>(in_d, rows, out_d, s);
+      else h->patch_to_emb_impl<float>(in_d, rows, out_d, s);
+    });
+  });
+}
+
 int64_t vb_last_launch_count(vb_handle* h) { return h ? h->last_launches : -1; }
 
 int vb_profile_enable(vb_handle* h, int32_t on) {
@@ -1260,6 +1558,38 @@ int vb_op_attention(int32_t precision, int32_t variant, const float* q, const fl
                                dim_head, variant, ma, mb, g, bt, 0);
       });
       download<T>(o_d, out, cq);
+    };
+    if (precision == VB_PRECISION_FP32) run(float());
+    else run(__nv_bfloat16());
+  });
+}
+
+int vb_op_patch_merger(int32_t precision, const float* x, const float* gamma, const float* beta, const float* queries, float* out,
+                       int32_t B, int32_t n, int32_t D, int32_t nt, int32_t iters, float* elapsed_ms) {
+  return guarded(nullptr, [&] {
+    require_gpu();
+    VB_CHECK(x && gamma && beta && queries && out && B > 0 && n > 0 && D > 0 && nt > 0, "vb_op_patch_merger: bad arguments");
+    DevMem dX, dG, dB, dQf, dY, dQ, dO, dS;
+    const float* g = upload<float>(dG, gamma, D);
+    const float* b = upload<float>(dB, beta, D);
+    const float* qf = upload<float>(dQf, queries, static_cast<size_t>(nt) * D);
+    const size_t cx = static_cast<size_t>(B) * n * D, co = static_cast<size_t>(B) * nt * D;
+    auto run = [&](auto tag) {
+      using T = decltype(tag);
+      const T* x_d = upload<T>(dX, x, cx);
+      dY.ensure(cx * sizeof(T) + 16); dQ.ensure(co * sizeof(T) + 16); dO.ensure(co * sizeof(T) + 16);
+      dS.ensure(static_cast<size_t>(B) * nt * ((n + 15) & ~15) * 4);
+      T* y_d = static_cast<T*>(dY.p);
+      T* q_d = static_cast<T*>(dQ.p);
+      T* o_d = static_cast<T*>(dO.p);
+      timed(iters, elapsed_ms, [&] {
+        layernorm<T>(x_d, D, g, b, y_d, D, B * n, D, 0);
+        broadcast_rows<T>(qf, q_d, B, nt, D, 0);
+        if (!attention_fast<T>(q_d, D, y_d, D, y_d, D, o_d, D, B, nt, n, 1, D, 0, nullptr, nullptr, nullptr, nullptr, 0))
+          attention_generic<T>(q_d, D, y_d, D, y_d, D, o_d, D, static_cast<float*>(dS.p), B, nt, n, 1, D, 0, nullptr, nullptr, nullptr,
+                               nullptr, 0);
+      });
+      download<T>(o_d, out, co);
     };
     if (precision == VB_PRECISION_FP32) run(float());
     else run(__nv_bfloat16());

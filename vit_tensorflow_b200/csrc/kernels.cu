@@ -444,6 +444,54 @@ __global__ void broadcast_row_kernel(const float* __restrict__ vec, T* __restric
   }
 }
 
+// dst[b, t, :] = vec[t, :] (fp32 [nt, D]) for every b: learned query rows shared by all images
+template <typename T>
+__global__ void broadcast_rows_kernel(const float* __restrict__ vec, T* __restrict__ dst, int B, int nt, int D) {
+  const long long per = static_cast<long long>(nt) * D, total = per * B;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[idx] = from_f<T>(vec[idx % per]);
+}
+
+// Soft split of T2T: tf.image.extract_patches(sizes k x k, strides s, rates 1, padding SAME) (t2t.py:43) followed by
+// 'b h w c -> b (h w) c' (:44).  One thread per output element; taps outside the image read 0; the patch vector is
+// (k_row, k_col, channel) with the channel fastest, so consecutive threads read consecutive channels of one input pixel.
+template <typename TI, typename TO>
+__global__ void unfold_same_kernel(const TI* __restrict__ in, TO* __restrict__ out, int B, int H, int W, int C, int k, int stride,
+                                   int oh, int ow, int pad_top, int pad_left, int cls_row, int ldo) {
+  const int rows = cls_row + oh * ow;
+  const int K = k * k * C;
+  const long long total = static_cast<long long>(B) * rows * ldo;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(idx % ldo);
+    const long long r = idx / ldo;
+    const int t = static_cast<int>(r % rows);
+    const long long b = r / rows;
+    float v = 0.f;
+    if (t >= cls_row && col < K) {
+      const int p = t - cls_row;
+      const int oy = p / ow, ox = p % ow;
+      const int c = col % C, kx = (col / C) % k, ky = col / (C * k);
+      const int y = oy * stride + ky - pad_top, x = ox * stride + kx - pad_left;
+      if (y >= 0 && y < H && x >= 0 && x < W) v = to_f(in[((b * H + y) * W + x) * C + c]);
+    }
+    out[idx] = from_f<TO>(v);
+  }
+}
+
+// out[r, c] = in[r, c] for c < cols, 0 for cols <= c < ldo (row-pitch change with conversion)
+template <typename TI, typename TO>
+__global__ void convert_rows_kernel(const TI* __restrict__ in, int ldi, TO* __restrict__ out, int ldo, long long rows, int cols) {
+  const long long total = rows * ldo;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % ldo);
+    const long long r = idx / ldo;
+    out[idx] = from_f<TO>(c < cols ? to_f(in[r * ldi + c]) : 0.f);
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long count) {
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < count;
@@ -645,6 +693,28 @@ void broadcast_row(const float* vec, T* dst, int dst_rows, int B, int D, cudaStr
   VB_LAUNCHED();
 }
 
+template <typename T>
+void broadcast_rows(const float* vec, T* dst, int B, int nt, int D, cudaStream_t s) {
+  broadcast_rows_kernel<T><<<grid_1d(static_cast<long long>(B) * nt * D), 256, 0, s>>>(vec, dst, B, nt, D);
+  VB_LAUNCHED();
+}
+
+template <typename TI, typename TO>
+void unfold_same(const TI* in, TO* out, int B, int H, int W, int C, int k, int stride, int cls_row, int ldo, cudaStream_t s) {
+  const int oh = (H + stride - 1) / stride, ow = (W + stride - 1) / stride;
+  const int ph = (oh - 1) * stride + k > H ? (oh - 1) * stride + k - H : 0, pw = (ow - 1) * stride + k > W ? (ow - 1) * stride + k - W : 0;
+  const long long total = static_cast<long long>(B) * (cls_row + oh * ow) * ldo;
+  unfold_same_kernel<TI, TO><<<grid_1d(total), 256, 0, s>>>(in, out, B, H, W, C, k, stride, oh, ow, ph / 2, pw / 2, cls_row, ldo);
+  VB_LAUNCHED();
+}
+
+template <typename TI, typename TO>
+void convert_rows(const TI* in, int ldi, TO* out, int ldo, long long rows, int cols, cudaStream_t s) {
+  if (rows == 0) return;
+  convert_rows_kernel<TI, TO><<<grid_1d(rows * ldo), 256, 0, s>>>(in, ldi, out, ldo, rows, cols);
+  VB_LAUNCHED();
+}
+
 template <typename TI, typename TO>
 void convert(const TI* in, TO* out, long long count, cudaStream_t s) {
   if (count == 0) return;
@@ -701,7 +771,10 @@ void row_stats_bf16(const __nv_bfloat16* X, int ldx, float* stats, int M, int D,
   template void attn_pv<T>(const float*, const T*, int, T*, int, int, int, int, int, int, cudaStream_t);                    \
   template void pool_layernorm<T>(const T*, int, int, const float*, const float*, float*, int, int, int, cudaStream_t);     \
   template void copy_tokens<T>(const T*, int, int, T*, int, int, int, int, int, cudaStream_t);                              \
-  template void broadcast_row<T>(const float*, T*, int, int, int, cudaStream_t);
+  template void broadcast_row<T>(const float*, T*, int, int, int, cudaStream_t);                                            \
+  template void broadcast_rows<T>(const float*, T*, int, int, int, cudaStream_t);                                           \
+  template void unfold_same<float, T>(const float*, T*, int, int, int, int, int, int, int, int, cudaStream_t);              \
+  template void convert_rows<float, T>(const float*, int, T*, int, long long, int, cudaStream_t);
 VB_INST_T(float)
 VB_INST_T(__nv_bfloat16)
 
@@ -710,6 +783,9 @@ template void gemm_simt<float, float, float>(const float*, int, const float*, in
 template void gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(const __nv_bfloat16*, int, const __nv_bfloat16*, int, int,
                                                                      __nv_bfloat16*, int, int, int, int, const float*,
                                                                      const float*, const __nv_bfloat16*, int, int, cudaStream_t);
+template void unfold_same<__nv_bfloat16, __nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int, int, int,
+                                                        cudaStream_t);
+template void convert_rows<__nv_bfloat16, float>(const __nv_bfloat16*, int, float*, int, long long, int, cudaStream_t);
 template void convert<float, __nv_bfloat16>(const float*, __nv_bfloat16*, long long, cudaStream_t);
 template void convert<__nv_bfloat16, float>(const __nv_bfloat16*, float*, long long, cudaStream_t);
 

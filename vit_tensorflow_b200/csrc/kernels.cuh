@@ -51,6 +51,20 @@ void copy_tokens(const T* src, int src_rows, int soff, T* dst, int dst_rows, int
 template <typename T>
 void broadcast_row(const float* vec, T* dst, int dst_rows, int B, int D, cudaStream_t s);
 
+// dst[b, t, :] = vec[t, :] (fp32 [nt, D]) for every b (PatchMerger queries, vit_with_patch_merger.py:47,51).
+template <typename T>
+void broadcast_rows(const float* vec, T* dst, int B, int nt, int D, cudaStream_t s);
+
+// T2T soft split (t2t.py:43-44): tf.image.extract_patches(sizes k, strides `stride`, rates 1, padding SAME) +
+// 'b h w c -> b (h w) c'.  in [B,H,W,C] (image or token map) -> out [B*(cls_row + oh*ow), ldo], oh = ceil(H/stride);
+// columns [0, k*k*C) hold the patch vector ((k_row, k_col, c), c fastest), [.., ldo) and the optional cls row are zero.
+template <typename TI, typename TO>
+void unfold_same(const TI* in, TO* out, int B, int H, int W, int C, int k, int stride, int cls_row, int ldo, cudaStream_t s);
+
+// out[r, 0:cols] = in[r, 0:cols], out[r, cols:ldo] = 0 (type conversion with a row-pitch change).
+template <typename TI, typename TO>
+void convert_rows(const TI* in, int ldi, TO* out, int ldo, long long rows, int cols, cudaStream_t s);
+
 template <typename TI, typename TO>
 void convert(const TI* in, TO* out, long long count, cudaStream_t s);
 void add_inplace_f32(float* a, const float* b, long long count, cudaStream_t s);

@@ -2,6 +2,9 @@
 
     ViT       vit_tensorflow/vit.py:106-177          DeepViT   vit_tensorflow/deepvit.py:112-157
     CaiT      vit_tensorflow/cait.py:155-194         CrossViT  vit_tensorflow/cross_vit.py:232-303
+    parallel_vit.ViT  parallel_vit.py:120-185        DistillableViT  distill.py:47-58 (forward)
+    T2TViT    vit_tensorflow/t2t.py:50-116           vit_with_patch_merger.ViT / PatchMerger  vit_with_patch_merger.py:42-55,134-185
+    efficient.ViT  vit_tensorflow/efficient.py:12-55 (injected transformer between the engine's embed and head stages)
 
 Same constructor kwargs, defaults and assertion messages; `model(img, training=True, **kwargs) -> logits`
 with `img` NHWC float32 `[b, H, W, 3]` and logits float32 `[b, num_classes]`.  Everything below the call is
@@ -62,6 +65,25 @@ class _Transformer:
 
     def __call__(self, x, training=True):
         return self._m.forward_tokens(x)
+
+
+class _Layer:
+    """A callable standing where the reference has a Keras layer (`patch_embedding.layers[i]`, `mlp_head`, `dropout`)."""
+
+    def __init__(self, fn):
+        self._fn = fn
+
+    def __call__(self, x, training=True):
+        return self._fn(x)
+
+
+class _PatchEmbedding(_Layer):
+    """`model.patch_embedding` (vit.py:141-144): Sequential([Rearrange, Dense]); the wrappers take `.layers[:2]` apart
+    (mae.py:37, simmim.py:79) or call `.layers[-1]` (mpp.py:200)."""
+
+    def __init__(self, model):
+        super().__init__(model.forward_patch_embedding)
+        self.layers = [_Layer(model.to_patch), _Layer(model.patch_to_emb)]
 
 
 class _EngineModel:
@@ -190,6 +212,82 @@ class _EngineModel:
                                                out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
         return out
 
+    # ---- the stages of `call` on their own ------------------------------------------
+    def _img(self, img):
+        x = np.ascontiguousarray(img, dtype=np.float32)
+        if x.ndim != 4 or x.shape[3] != 3:
+            raise ValueError("img must be NHWC float [b, H, W, 3]")
+        return x
+
+    def forward_embed(self, img):
+        """`call` up to the transformer (vit.py:160-166): patch embedding, cls token, positions -> [b, rows, dim]."""
+        self._finalize()
+        x = self._img(img)
+        b, h, w, _ = x.shape
+        rows = self._lib.vb_embed_rows(self._h, h, w)
+        if rows < 0:
+            _lib.check(-rows, self._h)
+        out = np.empty((b, rows, self._cfg.dim), np.float32)
+        _lib.check(self._lib.vb_forward_embed(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, h, w,
+                                              out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
+        return out
+
+    def forward_head(self, tokens):
+        """`call` after the transformer (vit.py:170-175): pooling + mlp_head; [b, n, dim] (or [b, dim]) -> logits."""
+        self._finalize()
+        x = np.ascontiguousarray(tokens, dtype=np.float32)
+        if x.ndim == 2:
+            x = x[:, None, :]
+        b, n, d = x.shape
+        if d != self._cfg.dim:
+            raise ValueError(f"tokens must have last dimension {self._cfg.dim}")
+        out = np.empty((b, self.num_classes), np.float32)
+        _lib.check(self._lib.vb_forward_head(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, n,
+                                             out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
+        return out
+
+    def to_patch(self, img):
+        """`patch_embedding.layers[0]`: Rearrange('b (h p1) (w p2) c -> b (h w) (p1 p2 c)') (vit.py:142)."""
+        x = self._img(img)
+        b, h, w, c = x.shape
+        ph, pw = self._cfg.patch_h, self._cfg.patch_w
+        if ph <= 0 or pw <= 0 or h % ph or w % pw:
+            raise ValueError("Image dimensions must be divisible by the patch size.")
+        out = np.empty((b, (h // ph) * (w // pw), ph * pw * c), np.float32)
+        _lib.check(self._lib.vb_to_patch(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, h, w,
+                                         out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
+        return out
+
+    def patch_to_emb(self, patches):
+        """`patch_embedding.layers[1]`: the Dense(dim) on patch vectors [..., patch_dim] (vit.py:143)."""
+        self._finalize()
+        x = np.ascontiguousarray(patches, dtype=np.float32)
+        pd = self._specs["patch.kernel"][0]
+        if x.shape[-1] != pd:
+            raise ValueError(f"patches must have last dimension {pd}")
+        rows = int(np.prod(x.shape[:-1]))
+        out = np.empty(x.shape[:-1] + (self._cfg.dim,), np.float32)
+        _lib.check(self._lib.vb_patch_to_emb(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, rows,
+                                             out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
+        return out
+
+    def forward_patch_embedding(self, img):
+        """`model.patch_embedding(img)` (vit.py:160)."""
+        if self._kind == "t2t_vit":
+            raise NotImplementedError("T2TViT: the tokens-to-token module runs inside forward_embed(img) (with cls token and "
+                                      "positions); only patch_embedding.layers[-1] (the Dense) is exposed separately")
+        return self.patch_to_emb(self.to_patch(img))
+
+    def _attach_stage_attributes(self):
+        """The attribute surface the reference's wrappers use: patch_embedding(.layers), pos_embedding,
+        cls_token, dropout, mlp_head."""
+        self.patch_embedding = _PatchEmbedding(self)
+        self.pos_embedding = _Tensorish(self, "pos_embedding")
+        if "cls_token" in self._specs:
+            self.cls_token = _Tensorish(self, "cls_token")
+        self.dropout = _Layer(lambda x: x)               # inference semantics: identity (vit.py:148,166)
+        self.mlp_head = _Layer(self.forward_head)
+
     PROFILE_CLASSES = ("gemm_tcgen05", "attention", "layernorm", "im2col", "other", "gemm_tcgen05_gelu", "gemm_tcgen05_residual")
 
     def profile(self, on=True):
@@ -235,8 +333,7 @@ class ViT(_EngineModel):
                      pool=0 if pool == 'cls' else 1)
         self.init_weights(seed)
         # attribute surface used by the reference's wrappers
-        self.pos_embedding = _Tensorish(self, "pos_embedding")
-        self.cls_token = _Tensorish(self, "cls_token")
+        self._attach_stage_attributes()
         self.transformer = _Transformer(self)
 
 
@@ -257,8 +354,7 @@ class ParallelViT(_EngineModel):
                      num_classes=num_classes, dim=dim, depth=depth, heads=heads, dim_head=dim_head, mlp_dim=mlp_dim,
                      pool=0 if pool == 'cls' else 1, parallel_branches=num_parallel_branches)
         self.init_weights(seed)
-        self.pos_embedding = _Tensorish(self, "pos_embedding")
-        self.cls_token = _Tensorish(self, "cls_token")
+        self._attach_stage_attributes()
 
 
 class DistillableViT(ViT):
@@ -320,8 +416,7 @@ class CaiT(_EngineModel):
                      num_classes=num_classes, dim=dim, depth=depth, cls_depth=cls_depth, heads=heads, dim_head=dim_head,
                      mlp_dim=mlp_dim)
         self.init_weights(seed)
-        self.pos_embedding = _Tensorish(self, "pos_embedding")
-        self.cls_token = _Tensorish(self, "cls_token")
+        self._attach_stage_attributes()
 
 
 class CrossViT(_EngineModel):
@@ -345,10 +440,128 @@ class CrossViT(_EngineModel):
         self.init_weights(seed)
 
 
+class T2TViT(_EngineModel):
+    """t2t.py:50-116.  `transformer=` injection (t2t.py:82-86): pass any callable over [b, n, dim] numpy tokens (e.g. another
+    engine model's `.transformer`); then depth / heads / mlp_dim may be omitted and the engine runs the tokens-to-token
+    module and the head around it."""
+    _kind = "t2t_vit"
+
+    def __init__(self, image_size, num_classes, dim, depth=None, heads=None, mlp_dim=None, pool='cls', channels=3, dim_head=64,
+                 dropout=0.0, emb_dropout=0.0, transformer=None, t2t_layers=((7, 4), (3, 2), (3, 2)), *, precision="bf16",
+                 device=0, seed=None):
+        assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
+        if transformer is None:
+            assert all(v is not None for v in (depth, heads, mlp_dim)), 'depth, heads, and mlp_dim must be supplied'
+        else:
+            depth, heads, mlp_dim = 0, 1, 1          # the engine holds no main-transformer layers
+        if channels != 3:
+            raise NotImplementedError("libvitb200 takes NHWC images with 3 channels")
+        if isinstance(image_size, tuple):
+            raise ValueError("T2TViT takes an integer image_size (t2t.py:66)")
+        t2t_layers = tuple((int(k), int(s)) for k, s in t2t_layers)
+        if not 1 <= len(t2t_layers) <= 4:
+            raise NotImplementedError("libvitb200 supports 1 to 4 t2t_layers")
+        self.num_classes, self.pool, self.dim = num_classes, pool, dim
+        self._dropout_rates = (dropout, emb_dropout)
+        kw = {}
+        for i, (k, s) in enumerate(t2t_layers):
+            kw[f"t2t_k{i}"], kw[f"t2t_s{i}"] = k, s
+        self._create(precision, device, image_h=image_size, image_w=image_size, num_classes=num_classes, dim=dim, depth=depth,
+                     heads=heads, dim_head=dim_head, mlp_dim=mlp_dim, pool=0 if pool == 'cls' else 1,
+                     t2t_num_layers=len(t2t_layers), **kw)
+        self.init_weights(seed)
+        self._attach_stage_attributes()
+        # t2t.py:58-74: patch_embedding is Sequential([RearrangeUnfoldTransformer..., Dense]); only its last layer (the Dense,
+        # what mpp.py:200 calls) is exposed on its own -- the soft splits run inside vb_forward_embed
+        self.patch_embedding.layers = [_Layer(self.patch_to_emb)]
+        self._injected = transformer
+        self.transformer = transformer if transformer is not None else _Transformer(self)
+
+    def __call__(self, img, training=True, **kwargs):
+        if self._injected is None:
+            return super().__call__(img, training=training)
+        self._check_training(training)
+        x = self.forward_embed(img)                                   # t2t.py:97-103
+        x = np.asarray(self._injected(x, training=training), dtype=np.float32)   # :105
+        return self.forward_head(x)                                   # :107-112
+
+    call = __call__
+
+
+class PatchMergerViT(_EngineModel):
+    """vit_with_patch_merger.py:134-185 (`vit_with_patch_merger.ViT`): no cls token, a PatchMerger after layer
+    `patch_merge_layer` (default depth // 2) shrinking the stream to `patch_merge_num_tokens` rows, mean pooling."""
+    _kind = "patch_merger_vit"
+
+    def __init__(self, image_size, patch_size, num_classes, dim, depth, heads, mlp_dim, patch_merge_layer=None,
+                 patch_merge_num_tokens=8, dim_head=64, dropout=0.0, emb_dropout=0.0, *, precision="bf16", device=0, seed=None):
+        image_height, image_width = pair(image_size)
+        patch_height, patch_width = pair(patch_size)
+        assert image_height % patch_height == 0 and image_width % patch_width == 0, 'Image dimensions must be divisible by the patch size.'
+        self.num_classes, self.dim = num_classes, dim
+        self._dropout_rates = (dropout, emb_dropout)
+        index = (patch_merge_layer if patch_merge_layer is not None else depth // 2) - 1   # vit_with_patch_merger.py:108
+        self._create(precision, device, image_h=image_height, image_w=image_width, patch_h=patch_height, patch_w=patch_width,
+                     num_classes=num_classes, dim=dim, depth=depth, heads=heads, dim_head=dim_head, mlp_dim=mlp_dim, pool=1,
+                     patch_merge_layer_index=index, patch_merge_num_tokens=patch_merge_num_tokens)
+        self.init_weights(seed)
+        self._attach_stage_attributes()
+
+
+class PatchMerger:
+    """vit_with_patch_merger.py:42-55 as a standalone layer: `PatchMerger(dim, num_tokens_out)(x [b, n, dim]) -> [b, num_tokens_out, dim]`.
+    Weights: `queries` N(0,1) [num_tokens_out, dim] (:47), `norm_gamma` / `norm_beta` (LayerNormalization :46)."""
+
+    def __init__(self, dim, num_tokens_out, *, precision="bf16", seed=None):
+        self.dim, self.num_tokens_out, self.precision = dim, num_tokens_out, precision
+        self.queries = np.random.default_rng(seed).standard_normal((num_tokens_out, dim)).astype(np.float32)
+        self.norm_gamma = np.ones(dim, np.float32)
+        self.norm_beta = np.zeros(dim, np.float32)
+
+    def __call__(self, x, training=True):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 3 or x.shape[2] != self.dim:
+            raise ValueError(f"x must be [b, n, {self.dim}]")
+        return _lib.op_patch_merger(x, self.norm_gamma, self.norm_beta, self.queries, precision=self.precision)[0]
+
+    call = __call__
+
+
+class EfficientViT(_EngineModel):
+    """efficient.py:12-55 (`efficient.ViT`): the ViT shell around an injected `transformer` -- any callable
+    `transformer(tokens [b, n + 1, dim], training=...) -> [b, n + 1, dim]` (the reference passes Keras layers from
+    efficient-attention libraries; another engine model's `.transformer` works too).  The engine runs the patch embedding,
+    cls token and positions (efficient.py:40-45, `vb_forward_embed`) and pooling + mlp_head (:48-55, `vb_forward_head`)."""
+    _kind = "vit"
+
+    def __init__(self, image_size, patch_size, num_classes, dim, transformer, pool='cls', *, precision="bf16", device=0, seed=None):
+        image_size_h, image_size_w = pair(image_size)
+        assert image_size_h % patch_size == 0 and image_size_w % patch_size == 0, 'image dimensions must be divisible by the patch size'
+        assert pool in {'cls', 'mean'}, 'pool type must be either cls (cls token) or mean (mean pooling)'
+        self.num_classes, self.pool, self.dim = num_classes, pool, dim
+        self._dropout_rates = ()
+        self._create(precision, device, image_h=image_size_h, image_w=image_size_w, patch_h=patch_size, patch_w=patch_size,
+                     num_classes=num_classes, dim=dim, depth=0, heads=1, dim_head=1, mlp_dim=1, pool=0 if pool == 'cls' else 1)
+        self.init_weights(seed)
+        self._attach_stage_attributes()
+        self.transformer = transformer
+
+    def __call__(self, img, training=True, **kwargs):
+        x = self.forward_embed(img)                                              # efficient.py:40-45
+        x = np.asarray(self.transformer(x, training=training), dtype=np.float32)  # :46
+        return self.forward_head(x)                                              # :48-55
+
+    call = __call__
+
+
 def from_config(cfg: dict, precision="bf16", device=0, seed=None):
     """Build a model from an oracle-style config dict (kind + reference kwargs)."""
-    kw = {k: v for k, v in cfg.items() if k not in ("kind", "channels", "image_h", "image_w", "patch_h", "patch_w", "num_patches")}
-    cls = {"vit": ViT, "deepvit": DeepViT, "cait": CaiT, "crossvit": CrossViT, "parallel_vit": ParallelViT}[cfg["kind"]]
+    kw = {k: v for k, v in cfg.items() if k not in ("kind", "channels", "image_h", "image_w", "patch_h", "patch_w", "num_patches",
+                                                    "patch_merge_layer_index", "t2t_dims")}
+    if cfg["kind"] == "patch_merger_vit":
+        kw.pop("pool", None)
+    cls = {"vit": ViT, "deepvit": DeepViT, "cait": CaiT, "crossvit": CrossViT, "parallel_vit": ParallelViT,
+           "patch_merger_vit": PatchMergerViT, "t2t_vit": T2TViT}[cfg["kind"]]
     if cfg["kind"] == "crossvit":
         kw.setdefault("dropout", 0.0)
         kw.setdefault("emb_dropout", 0.0)
