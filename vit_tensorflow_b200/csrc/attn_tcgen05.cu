@@ -28,6 +28,7 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
 #include <map>
 #include <tuple>
 
@@ -37,7 +38,10 @@ namespace {
 constexpr int DH = 64;
 constexpr int BQ = 128;          // query rows per tile (two tiles per work item)
 constexpr int BKV = 128;         // keys per block
-constexpr int KV_ST = 3;
+#ifndef VB_ATTN_KV_ST
+#define VB_ATTN_KV_ST 3
+#endif
+constexpr int KV_ST = VB_ATTN_KV_ST;   // K/V ring depth (3: 193 KB of shared memory, 4: 225 KB)
 constexpr int TILE_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr int P_BYTES = 2 * TILE_BYTES;      // 128 rows x 128 keys bf16 as two 64-column swizzled blocks
 constexpr int ATT_THREADS = 384;             // warps 0-3 / 4-7 softmax of tile 0 / 1, warp 8 TMA, warps 10-11 MMA issuers
@@ -46,11 +50,14 @@ constexpr int SMEM_DATA = 2 * TILE_BYTES /*Q*/ + KV_ST * 2 * TILE_BYTES /*K,V*/ 
 constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
 constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_PV + 64 t
+#ifndef VB_ATTN_STAGGER_DEFAULT
+#define VB_ATTN_STAGGER_DEFAULT 0            // cycles tile 1 starts after tile 0 (see the MMA issuer); VB_ATTN_STAGGER overrides
+#endif
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, int heads, int nq, int nk,
-                int num_items, float scale_log2, long long* __restrict__ dbg) {
+                int num_items, float scale_log2, int stagger, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -60,13 +67,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t bars = sP + 2 * P_BYTES;
   auto q_full = [&](int t) { return bars + 8u * t; };
   auto q_empty = [&](int t) { return bars + 16u + 8u * t; };
-  auto kv_full = [&](int s) { return bars + 32u + 8u * s; };
-  auto kv_empty = [&](int s) { return bars + 56u + 8u * s; };
-  auto s_full = [&](int t) { return bars + 80u + 8u * t; };
-  auto s_empty = [&](int t) { return bars + 96u + 8u * t; };
-  auto p_full = [&](int t) { return bars + 112u + 8u * t; };
-  auto pv_full = [&](int t) { return bars + 128u + 8u * t; };
-  const uint32_t tmem_slot = bars + 144u;
+  auto s_full = [&](int t) { return bars + 32u + 8u * t; };
+  auto s_empty = [&](int t) { return bars + 48u + 8u * t; };
+  auto p_full = [&](int t) { return bars + 64u + 8u * t; };
+  auto pv_full = [&](int t) { return bars + 80u + 8u * t; };
+  const uint32_t tmem_slot = bars + 96u;
+  auto kv_full = [&](int s) { return bars + 104u + 8u * s; };
+  auto kv_empty = [&](int s) { return bars + 104u + 8u * KV_ST + 8u * s; };   // <= 104 + 64 = 168 < 256 reserved bytes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pairs = (nq + 2 * BQ - 1) / (2 * BQ);
@@ -189,6 +196,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ++sn;
         return true;
       };
+      // Phase offset between the two tiles: both softmax groups share the SM's MUFU pipe (16 ex2/clk), and started together
+      // they run their exp phases at the same time (clock64 trace: 2.6 K cycles per 128-key block against 1.0 K of MUFU
+      // issue per warp) and then both leave it idle.  Tile 1 starts `stagger` cycles late so that its exp phases fall into
+      // tile 0's load / max / store phases; nothing but the K/V ring couples the tiles, so the offset persists.
+      if (t == 1 && stagger > 0) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < stagger) {}
+      }
       Cur cur = first();
       if (cur.ok) issue_s(cur, true);
       while (cur.ok) {
@@ -253,21 +268,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty(t));                           // the tensor core may overwrite S_t now
-        float mx = -INFINITY;
-        auto chunk_max = [&](int c, const uint32_t (&v)[32]) {             // full / partial / empty 32-key chunk
+        // row max: two independent chains per 32-key chunk (eight in flight) instead of one 64-deep dependent chain
+        auto chunk_max = [&](int c, const uint32_t (&v)[32]) -> float {    // full / partial / empty 32-key chunk
           const int nv = valid - c * 32;
+          float a = -INFINITY, b2 = -INFINITY;
           if (nv >= 32) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+            for (int i = 0; i < 32; i += 4) {
+              a = fmaxf(a, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+              b2 = fmaxf(b2, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            }
           } else if (nv > 0) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) mx = (i < nv) ? fmaxf(mx, __uint_as_float(v[i])) : mx;
+            for (int i = 0; i < 32; i += 2) {
+              a = (i < nv) ? fmaxf(a, __uint_as_float(v[i])) : a;
+              b2 = (i + 1 < nv) ? fmaxf(b2, __uint_as_float(v[i + 1])) : b2;
+            }
           }
+          return fmaxf(a, b2);
         };
-        chunk_max(0, v0);
-        chunk_max(1, v1);
-        chunk_max(2, v2);
-        chunk_max(3, v3);
+        const float mx = fmaxf(fmaxf(chunk_max(0, v0), chunk_max(1, v1)), fmaxf(chunk_max(2, v2), chunk_max(3, v3)));
         if (wq == 0 && lane == 0) trace(1 + t, 30 + j);
         const float m_blk = mx * scale_log2;
         // lazy reference update: exact as long as every exponent stays <= 2^8 above the reference
@@ -323,18 +343,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                            "r"(pk[3]) : "memory");
             }
           } else {
+            // partial chunk: the PV product reads whole 16-key steps, so only the 8-key groups below round_up(nv, 16) are
+            // written, and only those below nv cost MUFU work (n = 197: 8 exponentials for the 5 keys of the last chunk, not 32)
+            const int nv16 = (nv + 15) & ~15;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              uint32_t pk[4];
+              if (k * 8 >= nv16) break;
+              uint32_t pk[4] = {0u, 0u, 0u, 0u};
+              if (k * 8 < nv) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int e = k * 8 + 2 * i;
-                float x0, x1;
-                unpack2(fma2(pack2u(v[e], v[e + 1]), sc2, nm2), x0, x1);
-                const float p0 = (e < nv) ? ex2_approx(x0) : 0.f;
-                const float p1 = (e + 1 < nv) ? ex2_approx(x1) : 0.f;
-                rsum2 = add2(rsum2, pack2(p0, p1));
-                pk[i] = pack_bf16x2(p0, p1);
+                for (int i = 0; i < 4; ++i) {
+                  const int e = k * 8 + 2 * i;
+                  float x0, x1;
+                  unpack2(fma2(pack2u(v[e], v[e + 1]), sc2, nm2), x0, x1);
+                  const float p0 = (e < nv) ? ex2_approx(x0) : 0.f;
+                  const float p1 = (e + 1 < nv) ? ex2_approx(x1) : 0.f;
+                  rsum2 = add2(rsum2, pack2(p0, p1));
+                  pk[i] = pack_bf16x2(p0, p1);
+                }
               }
               const uint32_t slot = static_cast<uint32_t>(((c & 1) * 4 + k) ^ (row_local & 7));
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
@@ -450,6 +476,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   const int num_items = B * heads * pairs;
   const int grid = num_items < sm_count() ? num_items : sm_count();
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
+  static const int stagger = [] { const char* e = getenv("VB_ATTN_STAGGER"); return e ? atoi(e) : VB_ATTN_STAGGER_DEFAULT; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(ATT_THREADS);
@@ -461,7 +488,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, it->second.q, it->second.k, it->second.v, it->second.o, heads, nq, nk,
-                             num_items, scale_log2, attn_trace_buffer()));
+                             num_items, scale_log2, nq > BQ ? stagger : 0, attn_trace_buffer()));
   VB_CUDA(cudaGetLastError());
   count_launch();
   return true;
