@@ -565,10 +565,12 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   {
     const int sc_smem = (64 + ((nk + 7) & ~7)) * (dh + 8) * 2 + 32;   // +32: the last ldmatrix.x4 of a dh = 48 row touches its pad
-    static int configured = 0;
-    if (sc_smem > configured) {
+    static int configured[256] = {0};                               // per device: the attribute is device state
+    int dev = 0;
+    VB_CUDA(cudaGetDevice(&dev));
+    if (sc_smem > configured[dev & 255]) {
       VB_CUDA(cudaFuncSetAttribute(scores_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc_smem));
-      configured = sc_smem;
+      configured[dev & 255] = sc_smem;
     }
     scores_stripe_kernel<<<dim3((nq + 63) / 64, B * heads), 128, sc_smem, s>>>(q, ldq, k, ldk, S, heads, nq, nk, dh, scale, lds);
   }
@@ -587,13 +589,13 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
   const dim3 grid((nq + 63) / 64, B * heads);
   if (variant == 1) {
     constexpr int smem = 2 * (2 * 64 * 72 + 64 * (MAXDH + 8)) * 2;
-    static bool configured = false;
-    if (!configured) { VB_CUDA(cudaFuncSetAttribute(pv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    static unsigned long long seen[4] = {0, 0, 0, 0};
+    if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(pv_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     pv_rows_kernel<true><<<grid, 128, smem, s>>>(S, lds, nkp, v, ldv, out, ldo, heads, nq, nk, dh);
   } else {
     constexpr int smem = 2 * (64 * 72 + 64 * (MAXDH + 8)) * 2;
-    static bool configured = false;
-    if (!configured) { VB_CUDA(cudaFuncSetAttribute(pv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); configured = true; }
+    static unsigned long long seen[4] = {0, 0, 0, 0};
+    if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(pv_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     pv_rows_kernel<false><<<grid, 128, smem, s>>>(S, lds, nkp, v, ldv, out, ldo, heads, nq, nk, dh);
   }
   VB_CUDA(cudaGetLastError());
@@ -614,11 +616,8 @@ bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16*
   if (attention_rows_path(q, ldq, k, ldk, v, ldv, out, ldo, S, B, nq, nk, heads, dh, variant, mix_a, mix_b, ln_gamma, ln_beta, s)) return true;
   const size_t smem = (static_cast<size_t>(heads) * nk + 2 * heads * heads) * sizeof(float);
   if (smem > 200 * 1024) return false;
-  static bool configured = false;
-  if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(mid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  static unsigned long long seen[4] = {0, 0, 0, 0};
+  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(mid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   scores_mma_kernel<<<dim3((nk + 63) / 64, (nq + 63) / 64, B * heads), 128, 0, s>>>(q, ldq, k, ldk, S, heads, nq, nk, dh, scale, nk);
   VB_CUDA(cudaGetLastError());

@@ -454,11 +454,8 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
        reinterpret_cast<uintptr_t>(out)) % 16) return false;
-  static bool configured = false;
-  if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-    configured = true;
-  }
+  static unsigned long long seen[4] = {0, 0, 0, 0};
+  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   AttnKey key{q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads};
   auto& cache = plan_cache();
   auto it = cache.find(key);

@@ -30,6 +30,18 @@ struct Error : std::runtime_error {
 
 int sm_count();
 
+// Kernel function attributes (opt-in shared memory) are per DEVICE, and one process may hold handles on several GPUs:
+// true the first time the calling site runs on the current device.
+inline bool first_use_on_this_device(unsigned long long (&seen)[4]) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  unsigned long long& word = seen[(dev >> 6) & 3];
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (word & bit) return false;
+  word |= bit;
+  return true;
+}
+
 // 2-D / 3-D bf16 tensor maps (innermost dimension first), 128-byte swizzle unless swizzle == false.
 CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
                          uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true);

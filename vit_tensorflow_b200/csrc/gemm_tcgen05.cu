@@ -450,11 +450,8 @@ namespace {
 template <int BN, bool GELU, bool RES, int CG, int EPI>
 void launch(const GemmBf16& g, cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, GELU, RES, CG, EPI>;
-  static bool configured = false;
-  if (!configured) {
-    VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM_BYTES));
-    configured = true;
-  }
+  static unsigned long long seen[4] = {0, 0, 0, 0};
+  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM_BYTES));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.grid);
   cfg.blockDim = dim3(NUM_THREADS);
