@@ -50,14 +50,11 @@ constexpr int SMEM_DATA = 2 * TILE_BYTES /*Q*/ + KV_ST * 2 * TILE_BYTES /*K,V*/ 
 constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
 constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_PV + 64 t
-#ifndef VB_ATTN_STAGGER_DEFAULT
-#define VB_ATTN_STAGGER_DEFAULT 0            // cycles tile 1 starts after tile 0 (see the MMA issuer); VB_ATTN_STAGGER overrides
-#endif
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, int heads, int nq, int nk,
-                int num_items, float scale_log2, int stagger, long long* __restrict__ dbg) {
+                int num_items, float scale_log2, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -196,14 +193,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ++sn;
         return true;
       };
-      // Phase offset between the two tiles: both softmax groups share the SM's MUFU pipe (16 ex2/clk), and started together
-      // they run their exp phases at the same time (clock64 trace: 2.6 K cycles per 128-key block against 1.0 K of MUFU
-      // issue per warp) and then both leave it idle.  Tile 1 starts `stagger` cycles late so that its exp phases fall into
-      // tile 0's load / max / store phases; nothing but the K/V ring couples the tiles, so the offset persists.
-      if (t == 1 && stagger > 0) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < stagger) {}
-      }
       Cur cur = first();
       if (cur.ok) issue_s(cur, true);
       while (cur.ok) {
@@ -473,7 +462,6 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   const int num_items = B * heads * pairs;
   const int grid = num_items < sm_count() ? num_items : sm_count();
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
-  static const int stagger = [] { const char* e = getenv("VB_ATTN_STAGGER"); return e ? atoi(e) : VB_ATTN_STAGGER_DEFAULT; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(ATT_THREADS);
@@ -485,7 +473,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, it->second.q, it->second.k, it->second.v, it->second.o, heads, nq, nk,
-                             num_items, scale_log2, nq > BQ ? stagger : 0, attn_trace_buffer()));
+                             num_items, scale_log2, attn_trace_buffer()));
   VB_CUDA(cudaGetLastError());
   count_launch();
   return true;
