@@ -221,6 +221,21 @@ def test_patch_merger_never_merges_when_index_out_of_range(lib):
     np.testing.assert_allclose(m(img), oracle.forward_numpy(img, w, cfg), rtol=1e-3, atol=1e-4)
 
 
+@pytest.mark.parametrize("batch", [1, 7])
+@pytest.mark.parametrize("name", ["vit_small", "vit_mid", "cait_small"])
+def test_ragged_batches(lib, name, batch):
+    """Batch sizes that do not fill a 128-row GEMM tile (1 image) or leave a ragged last tile (7 images x 197 rows)."""
+    cfg = cfg_of(name)
+    w = oracle.stress_weights(cfg, 31)
+    img = oracle.make_image(cfg, batch, 32)
+    m = _model(cfg, "bf16")
+    m.set_weights_dict(w)
+    got = m(img, training=False)
+    ref = oracle.forward_numpy(img, w, cfg)
+    assert got.shape == (batch, cfg["num_classes"])
+    assert (np.abs(got - ref) <= BF16_ATOL + BF16_RTOL * np.abs(ref)).all()
+
+
 def test_batch_independence_and_determinism(lib):
     """Images are independent (no cross-sample op): logits of a batch equal logits of its halves, bit for bit,
     and repeated calls are bit-identical (what the data-parallel sharding relies on)."""
