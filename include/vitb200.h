@@ -10,7 +10,7 @@
  *     T2TViT(...)(img)               vit_tensorflow/t2t.py:50-54,96-116               
  *     vit_with_patch_merger.ViT(...)(img)   vit_tensorflow/vit_with_patch_merger.py:134-146,174-185   (8f, f4)
  *     efficient.ViT(...)(img)        vit_tensorflow/efficient.py:13-14,39-55 = vb_forward_embed -> caller's transformer -> vb_forward_head
- * and this header is what the Python host classes (vit_tensorflow_b200/*.py) bind with ctypes.
+ * and this header is what the Python host classes (vit_tensorflow_b200/models.py, _lib.py) bind with ctypes.
  * Plain pointers and sizes only; no torch / C++ types cross the boundary.
  *
  * Conventions
