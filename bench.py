@@ -57,7 +57,7 @@ def load_peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.limit")
 
     def __init__(self, index):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -89,7 +89,7 @@ class ClockSampler:
         self.f.flush()
         rows = [r.strip().split(",") for r in open(self.f.name) if r.strip()]
         os.unlink(self.f.name)
-        sm, mx, pw, reasons = [], [], [], set()
+        sm, mx, pw, reasons, limit = [], [], [], set(), None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
@@ -99,10 +99,14 @@ class ClockSampler:
             for n, v in zip(names, r[3:7]):
                 if v.strip().lower() == "active":
                     reasons.add(n)
+            try:
+                limit = float(r[7])      # enforced board power limit: boxes of this pool differ (about 500 W ... 1000 W)
+            except Exception:
+                pass
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
         busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
-        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), power_w_max=max(pw), samples=len(sm),
+        return dict(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), power_w_max=max(pw), power_limit_w=limit, samples=len(sm),
                     reasons=sorted(reasons))
 
 
@@ -319,7 +323,7 @@ def run_ours(args, c):
         sm = [c_["sm_mhz"] for c_ in all_clocks if c_.get("sm_mhz")]
         reasons = sorted(set(r for c_ in all_clocks for r in c_.get("reasons", [])))
         clocks_out = dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=clocks.get("sm_max_mhz"), reasons=reasons,
-                          power_w_max=clocks.get("power_w_max"))
+                          power_w_max=clocks.get("power_w_max"), power_limit_w=clocks.get("power_limit_w"))
         cb = None
         if world == 1 and not args.no_cpu_baseline:
             cb, _, _ = time_cpu_reference(c, budget_s=20.0, steps=3, warmup=1)

@@ -31,7 +31,8 @@ __device__ __forceinline__ float warp_max(float v) {
 inline int blocks_for(long long work, int per_block) { return static_cast<int>((work + per_block - 1) / per_block); }
 
 // ------------------------------------------------------------------------------------------ im2col
-// One thread per 4 consecutive output elements of a patch row segment (pw*C contiguous floats in the image).
+// One thread per 4 consecutive output elements of a patch row segment (pw*C contiguous floats in the image); the VEC4 form
+// keeps four independent 16-byte loads in flight per thread before the first store (ncu: 2.95 TB/s with one).
 template <typename T, bool VEC4>
 __global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out, int B, int H, int W, int C, int ph, int pw,
                               int cls_row, int ldo) {
@@ -40,44 +41,57 @@ __global__ void im2col_kernel(const float* __restrict__ img, T* __restrict__ out
   const int seg = pw * C;                 // contiguous run shared by input and output
   const int K = ph * seg;
   constexpr int V = VEC4 ? 4 : 1;
+  constexpr int U = VEC4 ? 4 : 1;         // units per thread per sweep
   const int units_per_row = ldo / V;      // ldo % 4 == 0 when VEC4
   const long long total = static_cast<long long>(B) * rows * units_per_row;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int u = static_cast<int>(idx % units_per_row);
-    const long long r = idx / units_per_row;
-    const int t = static_cast<int>(r % rows);
-    const int b = static_cast<int>(r / rows);
-    const int col = u * V;
-    float v[V];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long base = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; base < total; base += stride * U) {
+    float v[U][V];
+    T* dst[U];
 #pragma unroll
-    for (int i = 0; i < V; ++i) v[i] = 0.f;
-    if (t >= cls_row && col < K) {
-      const int p = t - cls_row;
-      const int py = p / gw, px = p % gw;
-      const int p1 = col / seg, off = col % seg;
-      const float* src = img + ((static_cast<long long>(b) * H + py * ph + p1) * W + px * pw) * C + off;
-      if (VEC4) {
-        const float4 f = *reinterpret_cast<const float4*>(src);   // seg % 4 == 0 -> never straddles a segment
-        v[0] = f.x; v[1 % V] = f.y; v[2 % V] = f.z; v[3 % V] = f.w;
-      } else {
-        v[0] = *src;
+    for (int u = 0; u < U; ++u) {
+      const long long idx = base + u * stride;
+#pragma unroll
+      for (int i = 0; i < V; ++i) v[u][i] = 0.f;
+      dst[u] = nullptr;
+      if (idx < total) {
+        const int un = static_cast<int>(idx % units_per_row);
+        const long long r = idx / units_per_row;
+        const int t = static_cast<int>(r % rows);
+        const int b = static_cast<int>(r / rows);
+        const int col = un * V;
+        dst[u] = out + r * ldo + col;
+        if (t >= cls_row && col < K) {
+          const int p = t - cls_row;
+          const int py = p / gw, px = p % gw;
+          const int p1 = col / seg, off = col % seg;
+          const float* src = img + ((static_cast<long long>(b) * H + py * ph + p1) * W + px * pw) * C + off;
+          if (VEC4) {
+            const float4 f = *reinterpret_cast<const float4*>(src);   // seg % 4 == 0 -> never straddles a segment
+            v[u][0] = f.x; v[u][1 % V] = f.y; v[u][2 % V] = f.z; v[u][3 % V] = f.w;
+          } else {
+            v[u][0] = *src;
+          }
+        }
       }
     }
-    T* dst = out + r * ldo + col;
-    if (VEC4) {
-      if (sizeof(T) == 4) {
-        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1 % V], v[2 % V], v[3 % V]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (dst[u] == nullptr) continue;
+      if (VEC4) {
+        if (sizeof(T) == 4) {
+          *reinterpret_cast<float4*>(dst[u]) = make_float4(v[u][0], v[u][1 % V], v[u][2 % V], v[u][3 % V]);
+        } else {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(v[u][0], v[u][1 % V]);
+          __nv_bfloat162 hi = __floats2bfloat162_rn(v[u][2 % V], v[u][3 % V]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(dst[u]) = pk;
+        }
       } else {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1 % V]);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(v[2 % V], v[3 % V]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(dst) = pk;
+        dst[u][0] = from_f<T>(v[u][0]);
       }
-    } else {
-      dst[0] = from_f<T>(v[0]);
     }
   }
 }
@@ -198,7 +212,7 @@ gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, in
                  int K, const float* __restrict__ bias, const float* __restrict__ scale, const TO* res, int ldr, int gelu) {
   constexpr int BMT = 16 * TM;
   __shared__ float As[16][BMT + 1];
-  __shared__ float Ws[16][64 + 1];
+  __shared__ __align__(16) float Ws[16][64 + 4];   // pitch 68 floats: 16-byte aligned rows, one LDS.128 per thread and k
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * BMT, n0 = blockIdx.x * 64;
   float acc[TM][4];
@@ -223,11 +237,13 @@ gemm_simt_kernel(const TA* __restrict__ A, int lda, const TW* __restrict__ W, in
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      float a[TM], w[4];
+      float a[TM];
 #pragma unroll
       for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) w[j] = Ws[kk][tx * 4 + j];
+      // the thread's four W columns in one 128-bit read (16 lanes x 16 B = two conflict-free wavefronts per warp; four
+      // scalar reads at pitch 65 cost eight): the TM = 1 classifier-head GEMM was shared-memory-bandwidth bound
+      const float4 w4 = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
