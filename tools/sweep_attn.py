@@ -31,7 +31,7 @@ for spec in specs:
     for st in [int(x) for x in (offs or "0").split(",")]:
         env = dict(os.environ, VB_LIB_PATH=lib, VB_ATTN_STAGGER=str(st))
         try:
-            r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=120)
+            r = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True, timeout=30)
             d = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:  # noqa: BLE001
             d = {"error": repr(e)[:200], "stderr": (r.stderr[-300:] if "r" in dir() else "")}
