@@ -50,22 +50,11 @@ constexpr int SMEM_DATA = 2 * TILE_BYTES /*Q*/ + KV_ST * 2 * TILE_BYTES /*K,V*/ 
 constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
 constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_PV + 64 t
-// VB_ATTN_SPLIT_Q = 1: the Q tile of query tile 1 gets its own producer (the spare warp 9), so the K/V ring no longer waits for
-// tile 1 to release its Q buffer and the two tiles are coupled by nothing but the ring depth.  Only then can a start-up phase
-// offset between the tiles (`stagger` cycles, VB_ATTN_STAGGER) persist: with one in-order producer the tiles re-align at every
-// item boundary (profiles/r01_attn_stagger_sweep.json).
-#ifndef VB_ATTN_SPLIT_Q
-#define VB_ATTN_SPLIT_Q 0
-#endif
-#ifndef VB_ATTN_STAGGER_DEFAULT
-#define VB_ATTN_STAGGER_DEFAULT 0
-#endif
-constexpr int ATT_Q1_WARP = 9;
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, int heads, int nq, int nk,
-                int num_items, float scale_log2, int stagger, long long* __restrict__ dbg) {
+                int num_items, float scale_log2, long long* __restrict__ dbg) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;
@@ -124,7 +113,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int h = bh % heads, b = bh / heads;
         const int row0 = pair * 2 * BQ;
         const int ntiles = (nq - row0 > BQ) ? 2 : 1;
-        for (int t = 0; t < (VB_ATTN_SPLIT_Q ? 1 : ntiles); ++t) {
+        for (int t = 0; t < ntiles; ++t) {
           mbar_wait(q_empty(t), (qcnt[t] & 1u) ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(q_full(t), TILE_BYTES);
@@ -145,23 +134,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           ++kv_cnt;
         }
       }
-    }
-  } else if (VB_ATTN_SPLIT_Q && warp == ATT_Q1_WARP) {
-    // ===================================================================== Q producer of tile 1 (split-producer form)
-    if (lane == 0) tma_prefetch_desc(&tmap_q);
-    uint32_t q1cnt = 0;
-    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
-      const int pair = it % pairs, bh = it / pairs;
-      const int h = bh % heads, b = bh / heads;
-      const int row0 = pair * 2 * BQ;
-      if (nq - row0 <= BQ) continue;                                       // this item has a single tile
-      mbar_wait(q_empty(1), (q1cnt & 1u) ^ 1u);
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full(1), TILE_BYTES);
-        tma_load_3d(sQ + TILE_BYTES, &tmap_q, q_full(1), h * DH, row0 + BQ, b);
-      }
-      __syncwarp();
-      ++q1cnt;
     }
   } else if (warp >= ATT_MMA_WARP0) {
     // ===================================================================== MMA issuer of tile t (warp-uniform loop)
@@ -221,10 +193,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         ++sn;
         return true;
       };
-      if (VB_ATTN_SPLIT_Q && t == 1 && stagger > 0) {                      // start-up phase offset of tile 1 (see VB_ATTN_SPLIT_Q)
-        const long long t0 = clock64();
-        while (clock64() - t0 < stagger) {}
-      }
       Cur cur = first();
       if (cur.ok) issue_s(cur, true);
       while (cur.ok) {
@@ -494,7 +462,6 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   const int num_items = B * heads * pairs;
   const int grid = num_items < sm_count() ? num_items : sm_count();
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
-  static const int stagger = [] { const char* e = getenv("VB_ATTN_STAGGER"); return e ? atoi(e) : VB_ATTN_STAGGER_DEFAULT; }();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(ATT_THREADS);
@@ -506,7 +473,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, it->second.q, it->second.k, it->second.v, it->second.o, heads, nq, nk,
-                             num_items, scale_log2, stagger, attn_trace_buffer()));
+                             num_items, scale_log2, attn_trace_buffer()));
   VB_CUDA(cudaGetLastError());
   count_launch();
   return true;
