@@ -181,7 +181,7 @@ def run_reference(args, c):
     cb, ms, b = time_cpu_reference(c, budget_s=150.0, steps=args.steps, warmup=args.warmup)
     line = dict(impl="reference", metric=METRIC, value=cb["value"], unit="images/s", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
-                data="synthetic", config=dict(workload=args.config, model=c["kind"], sample_batch=b,
+                data="synthetic", config=dict(workload=args.config, kind=c["kind"], sample_batch=b,
                                               note="CPU arm: the reference has no GPU/distributed path; rank 0 only"),
                 cpu_baseline=cb, e2e=dict(value=cb["value"], unit="images/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -330,7 +330,7 @@ def run_ours(args, c):
         line = dict(metric=METRIC, value=value, unit="images/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                     ms_per_step=ms_step, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
-                    config=dict(workload=args.config, model=c["kind"], per_gpu_batch=B, global_batch=world * B,
+                    config=dict(workload=args.config, kind=c["kind"], per_gpu_batch=B, global_batch=world * B,
                                 image=[H, W], parallelism=f"dp{world}", flops_per_image=flops_img,
                                 l2="inputs larger than L2 (154 MB images, >1 GB activations per step; no flush needed)",
                                 weights="random init (reference distributions), seed 0"),
