@@ -251,6 +251,22 @@ def test_batch_independence_and_determinism(lib):
     np.testing.assert_array_equal(full, halves)
 
 
+def test_full_size_batch_permutation_equivariance(lib):
+    """BASELINE.json configs[1] at full size (ViT-B/16 224^2, batch 256 -- far beyond what the CPU oracle finishes in seconds),
+    through a size-independent property of the path: images are independent, so permuting the batch permutes the logits, bit
+    for bit (M = 50 432 token rows = 394 full GEMM tiles whose boundaries fall inside images; every (image, head) attention
+    item lands on a different CTA).  Plus finiteness and a non-degenerate spread of the logits."""
+    cfg = oracle.make_config("vit", image_size=224, patch_size=16, num_classes=1000, dim=768, depth=12, heads=12, mlp_dim=3072)
+    m = _model(cfg, "bf16")                       # random init from the reference's distributions (host class, seed None)
+    rng = np.random.default_rng(7)
+    img = rng.standard_normal((256, 224, 224, 3), dtype=np.float32)
+    perm = rng.permutation(256)
+    a = m(img, training=False)
+    b = m(img[perm], training=False)
+    assert a.shape == (256, 1000) and np.isfinite(a).all() and a.std() > 1e-3
+    np.testing.assert_array_equal(a[perm], b)
+
+
 def test_dropout_training_semantics(lib):
     from vit_tensorflow_b200 import ViT
     m = ViT(image_size=32, patch_size=16, num_classes=4, dim=64, depth=1, heads=2, mlp_dim=64, dim_head=32, dropout=0.1,
