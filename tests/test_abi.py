@@ -72,6 +72,36 @@ def test_reference_assertions(lib):
         CaiT(image_size=32, patch_size=16, cls_depth=1, layer_dropout=0.05, **kw)
 
 
+def test_reference_assertions_of_the_8f_classes(lib):
+    # t2t.py:56,84 ; vit_with_patch_merger.py:154 ; efficient.py:18-19 -- raised by the host classes before any engine call
+    from vit_tensorflow_b200 import T2TViT, PatchMergerViT, EfficientViT
+    with pytest.raises(AssertionError, match="pool type must be either cls"):
+        T2TViT(image_size=32, num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32, pool="max")
+    with pytest.raises(AssertionError, match="depth, heads, and mlp_dim must be supplied"):
+        T2TViT(image_size=32, num_classes=4, dim=32)
+    with pytest.raises(AssertionError, match="Image dimensions must be divisible by the patch size."):
+        PatchMergerViT(image_size=30, patch_size=16, num_classes=4, dim=32, depth=2, heads=2, mlp_dim=32)
+    with pytest.raises(AssertionError, match="image dimensions must be divisible by the patch size"):
+        EfficientViT(image_size=30, patch_size=16, num_classes=4, dim=32, transformer=lambda x, training=True: x)
+    with pytest.raises(AssertionError, match="pool type must be either cls"):
+        EfficientViT(image_size=32, patch_size=16, num_classes=4, dim=32, transformer=lambda x, training=True: x, pool="max")
+
+
+def test_oracle_configs_of_the_8f_kinds():
+    import oracle
+    cfg = oracle.make_config("t2t_vit", image_size=224, num_classes=1000, dim=512, depth=5, heads=8, mlp_dim=512)
+    assert cfg["t2t_dims"] == (147, 1323, 11907) and cfg["num_patches"] == 196            # t2t.py:63,66 at the default t2t_layers
+    assert oracle.t2t_token_grid(cfg) == [(56, 56), (28, 28), (14, 14)]                   # SAME padding: ceil(size / stride)
+    specs = oracle.weight_specs(cfg)
+    assert specs["t2t.0.layers.0.to_qkv.kernel"][0] == (147, 441) and "t2t.0.layers.0.to_out.kernel" not in specs   # vit.py:53
+    assert specs["patch.kernel"][0] == (11907, 512) and specs["pos_embedding"][0] == (1, 197, 512)
+    pm = oracle.make_config("patch_merger_vit", image_size=256, patch_size=16, num_classes=1000, dim=1024, depth=12, heads=8, mlp_dim=2048,
+                            patch_merge_layer=6)
+    assert pm["patch_merge_layer_index"] == 5 and oracle.weight_specs(pm)["patch_merger.queries"][0] == (8, 1024)
+    assert oracle.make_config("patch_merger_vit", image_size=32, patch_size=16, num_classes=2, dim=8, depth=12, heads=1,
+                              mlp_dim=8)["patch_merge_layer_index"] == 5                   # default(None, depth // 2) - 1
+
+
 def test_drop_in_import_names():
     # README.md:47,148,177,325 of the reference
     from vit_tensorflow import ViT
@@ -80,6 +110,13 @@ def test_drop_in_import_names():
     from vit_tensorflow.cross_vit import CrossViT
     import vit_tensorflow_b200 as vb
     assert (ViT, DeepViT, CaiT, CrossViT) == (vb.ViT, vb.DeepViT, vb.CaiT, vb.CrossViT)
+    from vit_tensorflow.parallel_vit import ViT as PV
+    from vit_tensorflow.distill import DistillableViT
+    from vit_tensorflow.t2t import T2TViT
+    from vit_tensorflow.vit_with_patch_merger import ViT as PMV, PatchMerger
+    from vit_tensorflow.efficient import ViT as EV
+    assert (PV, DistillableViT, T2TViT, PMV, PatchMerger, EV) == (vb.ParallelViT, vb.DistillableViT, vb.T2TViT, vb.PatchMergerViT,
+                                                                   vb.PatchMerger, vb.EfficientViT)
 
 
 def test_built_for_sm100a_with_tcgen05(lib):
