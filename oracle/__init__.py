@@ -12,8 +12,11 @@ ships no tests / golden vectors.  The oracle is therefore
 restatement, made trustworthy by (1) two independent implementations -- a
 numpy-float64 "spec" (``spec_numpy``) and a torch-CPU-float32 restatement
 (``ref_torch``) -- that must agree, (2) einops itself (installed here) used as the
-ground truth for the patch ``Rearrange``, and (3) ``tools/ref_tf_dump.py``, a hook
-that dumps golden vectors from the real reference wherever TensorFlow exists.
+ground truth for the patch ``Rearrange``, (3) ``tools/ref_tf_dump.py``, a hook
+that dumps golden vectors from the real reference wherever TensorFlow exists, and
+(4) ``tests/test_oracle_vs_hf_vit.py``: the ViT restatement reproduces Hugging Face's
+independent PyTorch ``ViTForImageClassification`` on mapped weights (architecture and
+layouts, not Keras op semantics).
 """
 from .weights import (make_config, weight_specs, init_weights, stress_weights,  # noqa: F401
                       make_image, flops_per_image, t2t_token_grid)
