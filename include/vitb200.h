@@ -140,6 +140,23 @@ VB_API int vb_to_patch(vb_handle* h, const float* img, int32_t img_mem, int32_t 
 VB_API int vb_patch_to_emb(vb_handle* h, const float* patches, int32_t patches_mem, int32_t rows, float* out, int32_t out_mem,
                     void* stream);
 
+/* ---- data parallel: one handle per GPU (one process or thread each), the batch sharded contiguously, the
+ * forward free of communication, ONE in-place NCCL all-gather of the fp32 logits at the end.  The reference has no
+ * distributed path; these entries are what its maintainer would call from a multi-process launcher.  NCCL is loaded at
+ * vb_dp_init time with dlopen ($VB_NCCL_LIB, else libnccl.so.2): the library itself has no load-time NCCL dependency. ------ */
+
+/* Rank 0: fill id128 (128 bytes, an ncclUniqueId) and hand it to every rank by any transport (file, socket, MPI, gloo). */
+VB_API int vb_dp_unique_id(void* id128);
+
+/* Every rank (collective; blocks until all `world` ranks arrive): joins the handle's device to the communicator. */
+VB_API int vb_dp_init(vb_handle* h, const void* id128, int32_t rank, int32_t world);
+
+/* vb_forward on this rank's shard of `local_batch` images, its logits written straight into rows
+ * [rank*local_batch, (rank+1)*local_batch) of `gathered` (DEVICE float32 [world*local_batch, num_classes]), then
+ * ncclAllGather in place on `stream`.  Asynchronous on `stream`. */
+VB_API int vb_forward_allgather(vb_handle* h, const float* img, int32_t img_mem, int32_t local_batch, int32_t img_h, int32_t img_w,
+                         float* gathered, void* stream);
+
 /* Kernels launched by this handle's most recent forward call. */
 VB_API int64_t vb_last_launch_count(vb_handle* h);
 

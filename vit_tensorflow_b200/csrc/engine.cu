@@ -10,6 +10,8 @@
 #include "common.h"
 #include "kernels.cuh"
 
+#include <dlfcn.h>
+
 #include <array>
 #include <cmath>
 #include <cstdio>
@@ -123,9 +125,50 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 using namespace vb;
 
+// ------------------------------------------------------------------------------------------ NCCL (loaded on demand)
+// The five entry points of the NCCL 2.x C API the data-parallel path needs, declared here so that neither nccl.h nor a
+// link-time libnccl is required: ncclUniqueId is 128 opaque bytes passed by value, ncclComm_t an opaque pointer,
+// ncclFloat32 == 7, ncclSuccess == 0.
+namespace vb {
+namespace {
+struct NcclId { char internal[128]; };
+struct NcclApi {
+  int (*GetUniqueId)(NcclId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.ok) return api;
+  void* lib = nullptr;
+  if (const char* p = getenv("VB_NCCL_LIB")) lib = dlopen(p, RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (lib == nullptr) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  VB_CHECK(lib != nullptr, std::string("NCCL not found (set VB_NCCL_LIB to libnccl.so.2): ") + (dlerror() ? dlerror() : ""));
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  api.AllGather = reinterpret_cast<decltype(api.AllGather)>(dlsym(lib, "ncclAllGather"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  VB_CHECK(api.GetUniqueId && api.CommInitRank && api.AllGather && api.CommDestroy && api.GetErrorString,
+           "the NCCL library lacks one of ncclGetUniqueId / ncclCommInitRank / ncclAllGather / ncclCommDestroy / ncclGetErrorString");
+  api.ok = true;
+  return api;
+}
+void nccl_check(int rc, const char* what) {
+  if (rc != 0) throw vb::Error(5, std::string(what) + " failed: " + nccl().GetErrorString(rc));
+}
+}  // namespace
+}  // namespace vb
+
 struct vb_handle {
   vb_config cfg;
   int device = 0;
+  void* dp_comm = nullptr;          // ncclComm_t of the data-parallel group (vb_dp_init)
+  int dp_rank = 0, dp_world = 1;
   bool finalized = false;
   std::string error;
   std::vector<Weight> weights;
@@ -1427,6 +1470,44 @@ int vb_patch_to_emb(vb_handle* h, const float* patches, int32_t patches_mem, int
   });
 }
 
+int vb_dp_unique_id(void* id128) {
+  return guarded(nullptr, [&] {
+    VB_CHECK(id128 != nullptr, "vb_dp_unique_id: null argument");
+    NcclId id;
+    nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+    memcpy(id128, id.internal, sizeof id.internal);
+  });
+}
+
+int vb_dp_init(vb_handle* h, const void* id128, int32_t rank, int32_t world) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && id128 != nullptr, "vb_dp_init: null argument");
+    VB_CHECK(world >= 1 && rank >= 0 && rank < world, "vb_dp_init: need 0 <= rank < world");
+    VB_CHECK(h->dp_comm == nullptr, "vb_dp_init: the handle already belongs to a data-parallel group");
+    VB_CUDA(cudaSetDevice(h->device));
+    NcclId id;
+    memcpy(id.internal, id128, sizeof id.internal);
+    void* comm = nullptr;
+    nccl_check(nccl().CommInitRank(&comm, world, id, rank), "ncclCommInitRank");
+    h->dp_comm = comm; h->dp_rank = rank; h->dp_world = world;
+  });
+}
+
+int vb_forward_allgather(vb_handle* h, const float* img, int32_t img_mem, int32_t local_batch, int32_t img_h, int32_t img_w,
+                         float* gathered, void* stream) {
+  return guarded(h, [&] {
+    VB_CHECK(h != nullptr && img != nullptr && gathered != nullptr, "vb_forward_allgather: null argument");
+    VB_CHECK(h->dp_comm != nullptr, "vb_forward_allgather: call vb_dp_init first");
+    const size_t count = static_cast<size_t>(local_batch) * h->cfg.num_classes;
+    float* mine = gathered + static_cast<size_t>(h->dp_rank) * count;        // this rank's slice of the gather buffer
+    const int rc = vb_forward(h, img, img_mem, local_batch, img_h, img_w, mine, VB_MEM_DEVICE, stream);
+    if (rc != 0) throw vb::Error(rc, h->error);
+    // in place (sendbuff = recvbuff + rank * count), same stream: the head kernel's logits feed the collective directly
+    nccl_check(nccl().AllGather(mine, gathered, count, /*ncclFloat32*/ 7, h->dp_comm, static_cast<cudaStream_t>(stream)),
+               "ncclAllGather");
+  });
+}
+
 int64_t vb_last_launch_count(vb_handle* h) { return h ? h->last_launches : -1; }
 
 int vb_profile_enable(vb_handle* h, int32_t on) {
@@ -1458,6 +1539,7 @@ const char* vb_last_error(vb_handle* h) { return h ? h->error.c_str() : g_last_e
 void vb_destroy(vb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->dp_comm != nullptr) { nccl().CommDestroy(h->dp_comm); h->dp_comm = nullptr; }
   attention_mix_cache_clear();
   for (auto& w : h->weights) if (w.dev) cudaFree(w.dev);
   h->prof_collect();

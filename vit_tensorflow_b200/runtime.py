@@ -70,6 +70,60 @@ class DataParallel:
         return all_gather_logits(self.gathered, self.local, self.world)
 
 
+def default_nccl_library():
+    """The NCCL the engine should dlopen (`VB_NCCL_LIB`): the one bundled with torch when present, so that a process that
+    also uses torch.distributed shares a single libnccl."""
+    if os.environ.get("VB_NCCL_LIB"):
+        return os.environ["VB_NCCL_LIB"]
+    try:
+        import nvidia.nccl  # noqa: F401  (namespace package of the torch wheels)
+        cand = os.path.join(os.path.dirname(list(nvidia.nccl.__path__)[0] + "/"), "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            return cand
+    except Exception:
+        pass
+    return "libnccl.so.2"
+
+
+class NativeDataParallel:
+    """The same data-parallel group as `DataParallel`, but with the collective inside the C-ABI: `vb_dp_init` joins the
+    handle to an NCCL communicator and `vb_forward_allgather` runs the forward and the in-place all-gather of the logits on one
+    stream -- no torch.distributed on the data path.  The 128-byte communicator id travels by whatever the launcher has
+    (here: an already initialised torch.distributed group of any backend, or `id_bytes` passed in by the caller).
+    NOT yet exercised on a multi-GPU box (no multi-GPU minutes were left in round 1); `DataParallel` is the measured path."""
+
+    def __init__(self, model, per_rank_batch: int, image_hw, rank: int = 0, world: int = 1, id_bytes: bytes | None = None):
+        import ctypes as C
+        import torch
+        os.environ.setdefault("VB_NCCL_LIB", default_nccl_library())
+        self.model, self.B, (self.h, self.w) = model, per_rank_batch, image_hw
+        self.rank, self.world = rank, world
+        self.dev = torch.device("cuda", model.device)
+        lib = model._lib
+        if id_bytes is None:
+            import torch.distributed as dist
+            buf = (C.c_char * 128)()
+            if rank == 0:
+                _lib.check(lib.vb_dp_unique_id(buf))
+            box = [bytes(buf)]
+            if world > 1:
+                dist.broadcast_object_list(box, src=0)
+            id_bytes = box[0]
+        assert len(id_bytes) == 128
+        model._finalize()
+        _lib.check(lib.vb_dp_init(model._h, C.c_char_p(id_bytes), rank, world), model._h)
+        self.gathered = torch.empty((world * per_rank_batch, model.num_classes), dtype=torch.float32, device=self.dev)
+        self.local = self.gathered[rank * per_rank_batch:(rank + 1) * per_rank_batch]
+
+    def forward_device(self, img_dev):
+        import ctypes as C
+        import torch
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        _lib.check(self.model._lib.vb_forward_allgather(self.model._h, C.c_void_p(img_dev.data_ptr()), _lib.MEM_DEVICE, self.B, self.h,
+                                                        self.w, C.c_void_p(self.gathered.data_ptr()), C.c_void_p(stream)), self.model._h)
+        return self.gathered
+
+
 class HostPipeline:
     """Host batches in -> host logits out, the call a serving user makes.
 
