@@ -52,37 +52,62 @@ def main():
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, repo)
     sys.path.insert(0, os.path.join(repo, "tests"))
+    import importlib
     import oracle
     from cases import SMALL
-    from vit import ViT
-    from deepvit import DeepViT
-    from cait import CaiT
+    # reference module and class per oracle kind (flat imports: `from vit import Transformer` inside t2t.py etc.)
+    classes = {"vit": ("vit", "ViT"), "deepvit": ("deepvit", "DeepViT"), "cait": ("cait", "CaiT"),
+               "parallel_vit": ("parallel_vit", "ViT"), "patch_merger_vit": ("vit_with_patch_merger", "ViT"), "t2t_vit": ("t2t", "T2TViT")}
 
     for name, d in SMALL.items():
         kw = dict(d)
         kind = kw.pop("kind")
-        if kind == "crossvit":
-            continue  # same recipe; attribute paths in SURVEY.md App. B
+        if kind not in classes:
+            print(name, "skipped (CrossViT: same recipe; attribute paths in SURVEY.md App. B)")
+            continue
         cfg = oracle.make_config(kind, **kw)
         w = oracle.stress_weights(cfg, 11)
         img = oracle.make_image(cfg, 2, 12)
-        model = {"vit": ViT, "deepvit": DeepViT, "cait": CaiT}[kind](**kw)
+        mod, cls = classes[kind]
+        model = getattr(importlib.import_module(mod), cls)(**kw)
         model(img, training=False)  # build variables
         model.pos_embedding.assign(w["pos_embedding"])
-        model.cls_token.assign(w["cls_token"])
-        _set_dense(model.patch_embedding.layers[1], w, "patch")
-        if kind == "cait":
+        if "cls_token" in w:
+            model.cls_token.assign(w["cls_token"])
+        if kind == "t2t_vit":
+            # t2t.py:58-74: Sequential([RearrangeUnfoldTransformer, ..., Dense]); every soft split but the last owns
+            # `transformer_layer` = vit.Transformer(depth=1)
+            stages = model.patch_embedding.layers
+            for i, st in enumerate(stages[:-2]):
+                attn, ff = st.transformer_layer.layers[0]
+                _set_vit_layer(attn, ff, w, f"t2t.{i}.layers.0.", "vit")
+            _set_dense(stages[-1], w, "patch")
+        else:
+            _set_dense(model.patch_embedding.layers[1], w, "patch")
+        if kind == "parallel_vit":
+            # parallel_vit.py:109-112: layers[L] = [Parallel(attention fns), Parallel(feed-forward fns)]
+            for L, (attns, ffs) in enumerate(model.transformer.layers):
+                for i, (attn, ff) in enumerate(zip(attns.fns, ffs.fns)):
+                    _set_vit_layer(attn, ff, w, f"layers.{L}.branch{i}.", "vit")
+        elif kind == "patch_merger_vit":
+            for L, (attn, ff) in enumerate(model.transformer.layers):
+                _set_vit_layer(attn, ff, w, f"layers.{L}.", "vit")
+            pm = model.transformer.patch_merger                         # vit_with_patch_merger.py:42-47
+            pm.queries.assign(w["patch_merger.queries"])
+            _set_ln(pm.norm, w, "patch_merger.norm")
+        elif kind == "cait":
             for stack in ("patch_transformer", "cls_transformer"):
                 for L, (attn, ff) in enumerate(getattr(model, stack).layers):
                     pre = f"{stack}.layers.{L}."
                     attn.scale.assign(w[pre + "attn_scale"])
                     ff.scale.assign(w[pre + "ff_scale"])
                     _set_vit_layer(attn.fn, ff.fn, w, pre, "cait")
-        else:
+        else:   # vit, deepvit, t2t_vit: vit.Transformer / deepvit.Transformer layers
             for L, (attn, ff) in enumerate(model.transformer.layers):
-                _set_vit_layer(attn, ff, w, f"layers.{L}.", kind)
-        _set_ln(model.mlp_head.layers[0], w, "head_norm")
-        _set_dense(model.mlp_head.layers[1], w, "head")
+                _set_vit_layer(attn, ff, w, f"layers.{L}.", "vit" if kind == "t2t_vit" else kind)
+        head = model.mlp_head.layers                                    # patch-merger ViT: [Reduce, LayerNormalization, Dense]
+        _set_ln(head[-2], w, "head_norm")
+        _set_dense(head[-1], w, "head")
         logits = model(img, training=False).numpy()
         np.savez(os.path.join(out_dir, f"{name}__tf.npz"), logits_tf=logits,
                  meta=json.dumps(dict(config=d, weights="stress_weights", weight_seed=11, image_seed=12, batch=2)))
