@@ -66,6 +66,8 @@ def main():
             try:
                 r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, ops=ops, iters=args.iters, shapes=SHAPES)], env=env,
                                    capture_output=True, text=True, timeout=60 + 10 * len(ops))
+                if r.returncode != 0 or not r.stdout.strip():
+                    raise RuntimeError((r.stderr or "no output").strip().splitlines()[-1])
                 rec["ops"] = json.loads(r.stdout.strip().splitlines()[-1])
             except Exception as e:  # noqa: BLE001
                 rec["error"] = repr(e)[:300]
