@@ -35,6 +35,9 @@ constexpr int UMMA_K = 16;
 #ifndef VB_GEMM_EW
 #define VB_GEMM_EW 2                     // epilogue warps per TMEM lane quarter for 256-wide tiles (2 or 3)
 #endif
+#ifndef VB_GEMM_STORE_WAIT1
+#define VB_GEMM_STORE_WAIT1 0
+#endif
 constexpr int MAX_EPI_WARPS = 4 * VB_GEMM_EW;   // epilogue warps (TMEM lane quarter = warp % 4, chunk lane = warp / 4)
 constexpr int PRODUCER_WARP = MAX_EPI_WARPS;    // the issue arbiter favours high warp ids: keep the two latency-critical
 constexpr int MMA_WARP = MAX_EPI_WARPS + 1;     // single-instruction-stream roles above the math-heavy epilogue warps
@@ -305,7 +308,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // the OTHER slab was last read by the TMA store of the previous chunk: once that has drained, prefetch the next
         // chunk's residual into it (or simply make it writable again)
         if (lane == 0) {
-          bulk_wait_group_read<0>();
+          // VB_GEMM_STORE_WAIT1 (experiment, off): without a residual prefetch only the slab of TWO chunks ago is about to
+          // be overwritten, so the store issued a moment ago may stay in flight
+          if (!RES && VB_GEMM_STORE_WAIT1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
           if (RES) res_issue(cnt + 1);
         }
         tmem_ld_wait();
