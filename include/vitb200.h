@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define VB_ABI_VERSION 3
+#define VB_ABI_VERSION 4
 #if defined(__GNUC__)
 #define VB_API __attribute__((visibility("default")))
 #else
@@ -199,6 +199,13 @@ VB_API int vb_op_layernorm(int32_t precision, const float* x, const float* gamma
  * -> out [B,nt,D]. */
 VB_API int vb_op_patch_merger(int32_t precision, const float* x, const float* gamma, const float* beta, const float* queries,
                        float* out, int32_t B, int32_t n, int32_t D, int32_t nt, int32_t iters, float* elapsed_ms);
+
+/* PreNorm + Dense as the bf16 engine runs it (vit.py:18-22 followed by vit.py:39 / :59): LayerNorm over the last axis
+ * (eps 1e-3) FOLDED into the following Dense -- gamma scaled into the packed weights, the per-row (mean, rstd) reduced in
+ * the GEMM epilogue from (sum, sumsq) partials of the bf16 rows.  x [M,K], w [K,N] (Keras layout), bias [N] or NULL,
+ * out [M,N] = act(LN(x) w + bias), act = exact-erf GELU when gelu != 0.  bf16 engine only; N % 64 == 0, K % 64 == 0. */
+VB_API int vb_op_ln_linear(const float* x, const float* gamma, const float* beta, const float* w, const float* bias,
+                    int32_t gelu, float* out, int32_t M, int32_t N, int32_t K, int32_t iters, float* elapsed_ms);
 
 #ifdef __cplusplus
 }

@@ -23,7 +23,7 @@ def test_header_symbols_are_exported_and_bound(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/vitb200.h but not exported"
     assert sorted(_lib.SIGNATURES) == declared, "ctypes SIGNATURES must cover exactly the declared ABI"
-    assert lib.vb_abi_version() == 3
+    assert lib.vb_abi_version() == 4
 
 
 def test_config_struct_layout_matches_header():
@@ -150,3 +150,42 @@ def test_built_for_sm100a_with_tcgen05(lib):
     assert "sm_100a" in sass
     for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
         assert mnemonic in sass, mnemonic
+
+
+def test_attribute_surface_supports_the_wrapper_expressions():
+    """`model.pos_embedding` / `model.cls_token` as mae.py:54, simmim.py:95, mpp.py:204-208 use them (slicing, einops repeat,
+    arithmetic).  They are properties over the model's weight dict, so a stub holding `_specs` / `_weights` is enough on a CPU
+    box (constructing a real model needs a B200)."""
+    import numpy as np
+    from einops import repeat
+    from vit_tensorflow_b200.models import _EngineModel
+
+    class Stub(_EngineModel):
+        def __init__(self):
+            rng = np.random.default_rng(0)
+            self._weights = {"pos_embedding": rng.standard_normal((1, 17, 8)).astype(np.float32),
+                             "cls_token": rng.standard_normal((1, 1, 8)).astype(np.float32)}
+            self._specs = {k: v.shape for k, v in self._weights.items()}
+
+        def __del__(self):
+            pass
+
+    m = Stub()
+    w = m._weights
+    n, b = 9, 3
+    tokens = np.ones((b, n, 8), np.float32)
+    assert m.pos_embedding.shape == (1, 17, 8) and m.pos_embedding.shape[-2:] == (17, 8)                   # mae.py:33
+    np.testing.assert_array_equal(tokens + m.pos_embedding[:, 1:(n + 1)], tokens + w["pos_embedding"][:, 1:n + 1])   # mae.py:54, simmim.py:95
+    np.testing.assert_array_equal(m.pos_embedding[:, :(n + 1)], w["pos_embedding"][:, :n + 1])             # mpp.py:208
+    c = repeat(m.cls_token, '() n d -> b n d', b=b)                                                        # mpp.py:204
+    assert c.shape == (b, 1, 8)
+    np.testing.assert_array_equal(np.concatenate([c, tokens], axis=1)[:, 0], np.broadcast_to(w["cls_token"][0], (b, 8)))
+    np.testing.assert_array_equal(2.0 * m.pos_embedding + 1.0, 2.0 * w["pos_embedding"] + 1.0)
+    w["pos_embedding"] = np.zeros((1, 17, 8), np.float32)                                                  # a newly set weight is seen
+    assert float(np.abs(m.pos_embedding).max()) == 0.0
+    del m._specs["cls_token"]                                                                              # CaiT-less models: AttributeError
+    try:
+        m.cls_token
+        raise AssertionError("expected AttributeError")
+    except AttributeError:
+        pass

@@ -269,10 +269,9 @@ def test_full_size_batch_permutation_equivariance(lib):
 
 def test_native_dp_single_rank_allgather(lib, tmp_path):
     """vb_dp_init / vb_forward_allgather (SURVEY.md 8e through the C-ABI itself) with a world of one rank: the in-place
-    ncclAllGather must leave exactly vb_forward's logits in the gather buffer.  Runs in a child process with a time limit and is
-    reported as an expected failure instead of an error if NCCL cannot initialise on this box: the entry points were written
-    when no multi-GPU (or spare single-GPU) minutes were left, so `runtime.DataParallel` (torch.distributed) remains the
-    measured path until a round validates this one on 2+ GPUs."""
+    ncclAllGather must leave exactly vb_forward's logits in the gather buffer.  Runs in a child process (its own NCCL
+    communicator, with a time limit); any failure fails the test.  The 2-GPU form of the same check is
+    tools/dp_check.py, run under `gpurun --gpus 2` (profiles/r02_dp_check_*.txt)."""
     import subprocess
     import sys
     code = r"""
@@ -291,12 +290,8 @@ torch.cuda.synchronize()
 np.testing.assert_array_equal(out.cpu().numpy(), ref)
 print("native dp ok")
 """ % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    try:
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
-    except subprocess.TimeoutExpired:
-        pytest.xfail("native NCCL data-parallel path timed out on this box (not yet validated)")
-    if r.returncode != 0 or "native dp ok" not in r.stdout:
-        pytest.xfail("native NCCL data-parallel path failed on this box (not yet validated): " + r.stderr[-400:])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "native dp ok" in r.stdout, "native NCCL data-parallel path failed:\n" + r.stdout[-400:] + r.stderr[-1200:]
 
 
 def test_dropout_training_semantics(lib):

@@ -138,8 +138,105 @@ def test_attention(lib, precision, variant, B, nq, nk, heads, dh):
     if precision == "fp32":
         np.testing.assert_allclose(out, ref, rtol=2e-4, atol=2e-4)
     else:
-        # P is rounded to bf16 before the PV product on the tensor-core path: 2^-8 relative per probability
-        np.testing.assert_allclose(out, ref, rtol=2e-2, atol=3e-2)
+        # P (and DeepViT's re-attention weights) are rounded to bf16 before the PV product on the tensor-core paths and the
+        # output is stored as bf16: both are 2^-9 relative.  The bound is stated against the spread of the output (sigma_out:
+        # ~0.07 for plain softmax over N(0,1) scores at n = 577, ~14 for DeepViT's O(1) re-attention weights), not against 1.
+        _assert_close_sigma(out, ref, ATTN_BF16_SIGMA[variant], ATTN_BF16_REL)
+
+
+# bf16 attention bound: |err| <= SIGMA * std(ref) + REL * |ref|  (measured maxima: DESIGN.md section 6)
+ATTN_BF16_SIGMA = {0: 1.5e-2, 1: 1.5e-2, 2: 1.5e-2}
+ATTN_BF16_REL = 1.0e-2
+
+
+def _assert_close_sigma(out, ref, sigma_frac, rel):
+    err = np.abs(out - ref)
+    sig = float(ref.std())
+    bound = sigma_frac * sig + rel * np.abs(ref)
+    worst = float((err / bound).max())
+    print(f"\n[attention bf16] max err {err.max():.3e}, sigma_out {sig:.3e}, max err / sigma_out {err.max() / sig:.3e}, "
+          f"worst err / bound {worst:.3f}")
+    assert worst <= 1.0, f"max err {err.max():.4e} at sigma_out {sig:.4e}: {worst:.2f} x the bound"
+
+
+@pytest.mark.parametrize("ramp", ["up", "down", "zigzag"])
+@pytest.mark.parametrize("B,n,heads", [(2, 577, 2), (3, 197, 3), (1, 300, 1)])
+def test_attention_lazy_rescale(lib, B, n, heads, ramp):
+    """The tcgen05 kernel keeps its softmax reference point until a 128-key block's row max exceeds it by more than 2^8 and
+    only then rescales O in tensor memory (attn_tcgen05.cu, `need`).  N(0,1) scores never do that, so this case scales the
+    keys of block j by a ramp: with 'up' every later block beats the running reference by ~15 in log2 units (the rescale and
+    the l correction run for every j > 0), 'down' keeps the first block's reference throughout (later exponents underflow
+    towards 0), 'zigzag' alternates."""
+    from vit_tensorflow_b200 import _lib
+    dh = 64
+    rng = np.random.default_rng(n + heads)
+    inner = heads * dh
+    q = bf16_round(rng.standard_normal((B, n, inner), dtype=np.float32))
+    k = rng.standard_normal((B, n, inner), dtype=np.float32)
+    v = bf16_round(rng.standard_normal((B, n, inner), dtype=np.float32))
+    nblk = (n + 127) // 128
+    f = {"up": [1 + 4 * j for j in range(nblk)], "down": [1 + 4 * (nblk - 1 - j) for j in range(nblk)],
+         "zigzag": [1 + 6 * (j % 2) + j for j in range(nblk)]}[ramp]
+    for j in range(nblk):
+        k[:, j * 128:(j + 1) * 128] *= f[j]
+    k = bf16_round(k)
+    out, _ = _lib.op_attention(q, k, v, heads, 0, precision="bf16")
+    ref = _attention_ref(q, k, v, heads, 0, None, None, None, None)
+    # the ramp must really cross the kernel's threshold (8 in log2 units after the dh^-0.5 * log2(e) scaling) ...
+    sp = lambda t: t.reshape(B, n, heads, dh).transpose(0, 2, 1, 3).astype(np.float64)
+    s2 = np.einsum('bhid,bhjd->bhij', sp(q), sp(k)) * dh ** -0.5 * 1.4426950408889634
+    bm = np.stack([s2[..., j * 128:(j + 1) * 128].max(-1) for j in range(nblk)], -1)      # [B, h, n, nblk] block row maxima
+    run = np.maximum.accumulate(bm, -1)
+    crossed = (bm[..., 1:] > run[..., :-1] + 8.0)
+    if ramp != "down":
+        assert crossed.any(-1).mean() > 0.9, "test construction: the ramp does not trigger the lazy rescale"
+    else:
+        assert not crossed.any()
+    _assert_close_sigma(out, ref, 1.5e-2, 1.0e-2)
+
+
+def _ln_linear_ref(x, g, b, w, bias, gelu):
+    x64 = x.astype(np.float64)
+    mu = x64.mean(-1, keepdims=True)
+    var = ((x64 - mu) ** 2).mean(-1, keepdims=True)
+    y = (x64 - mu) / np.sqrt(var + 1e-3) * g + b
+    r = y @ w.astype(np.float64)
+    if bias is not None:
+        r = r + bias
+    return _gelu(r) if gelu else r, y
+
+
+@pytest.mark.parametrize("gelu", [False, True])
+@pytest.mark.parametrize("rows", ["normal", "offset50", "outliers"])
+@pytest.mark.parametrize("M,N,K", [(394, 768, 768), (1000, 3072, 1024), (130, 192, 384)])
+def test_ln_folded_linear(lib, M, N, K, rows, gelu):
+    """PreNorm + Dense as the bf16 engine runs it (vit.py:18-22 + :39/:59): LayerNorm folded into the GEMM, its (mean, rstd)
+    reduced in the epilogue from one-pass fp32 (sum, sumsq) partials of the bf16 rows.  `offset50`: rows of mean 50 and
+    sigma 1 (E[x^2] - mu^2 cancels 3.4 digits); `outliers`: additionally four channels two orders of magnitude above the
+    rest, as trained ViTs have.  Reference: float64 LayerNorm + matmul on the same bf16-rounded rows."""
+    from vit_tensorflow_b200 import _lib
+    rng = np.random.default_rng(M + K)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    if rows != "normal":
+        x += 50.0
+    if rows == "outliers":
+        cols = rng.choice(K, 4, replace=False)
+        x[:, cols] = (100.0 * (50.0 + rng.standard_normal((M, 4)))).astype(np.float32)
+    x = bf16_round(x)
+    g = rng.uniform(0.5, 1.5, K).astype(np.float32)
+    b = (0.2 * rng.standard_normal(K)).astype(np.float32)
+    w = (rng.standard_normal((K, N)) / np.sqrt(K)).astype(np.float32)
+    bias = (0.2 * rng.standard_normal(N)).astype(np.float32)
+    out, _ = _lib.op_ln_linear(x, g, b, w, bias, gelu)
+    ref, y = _ln_linear_ref(x, g, b, w, bias, gelu)
+    # bf16 weights (2^-9 relative each, K random terms) + bf16 output rounding; the activations enter exactly.
+    # natural scale of one output: |y| . |w| summed in quadrature = sqrt(sum_k y_k^2 w_kn^2)
+    scale = np.sqrt((y ** 2) @ (w.astype(np.float64) ** 2))
+    err = np.abs(out - ref)
+    bound = 2.0 ** -7 * np.abs(ref) + 2.0 ** -6 * scale + 1e-3
+    worst = float((err / bound).max())
+    print(f"\n[ln-folded linear {rows}] max err {err.max():.3e}, max |ref| {np.abs(ref).max():.3e}, worst err / bound {worst:.3f}")
+    assert worst <= 1.0
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

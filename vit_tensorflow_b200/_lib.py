@@ -64,6 +64,7 @@ SIGNATURES = {
     "vb_op_attention": (C.c_int, [C.c_int32, C.c_int32] + [C.c_void_p] * 8 + [C.c_int32] * 6 + [_f32p]),
     "vb_op_layernorm": (C.c_int, [C.c_int32] + [C.c_void_p] * 4 + [C.c_int32] * 3 + [_f32p]),
     "vb_op_patch_merger": (C.c_int, [C.c_int32] + [C.c_void_p] * 5 + [C.c_int32] * 5 + [_f32p]),
+    "vb_op_ln_linear": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_void_p] + [C.c_int32] * 4 + [_f32p]),
 }
 
 _lib = None
@@ -81,7 +82,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        if lib.vb_abi_version() != 3:
+        if lib.vb_abi_version() != 4:
             raise VbError("libvitb200 ABI version mismatch")
         _lib = lib
     return _lib
@@ -132,6 +133,18 @@ def op_layernorm(x, gamma, beta, precision="bf16", iters=0):
     out = np.empty_like(x)
     ms = C.c_float(0)
     check(load().vb_op_layernorm(PRECISION[precision], _ptr(x), _ptr(gamma), _ptr(beta), _ptr(out), M, D, iters, C.byref(ms)))
+    return out, (ms.value if iters > 0 else None)
+
+
+def op_ln_linear(x, gamma, beta, w, bias=None, gelu=False, iters=0):
+    """out = act(LayerNorm(x) @ w + bias) through the LayerNorm-folded tcgen05 GEMM (bf16 engine); returns (out, ms)."""
+    x, gamma, beta, w, bias = map(_f32, (x, gamma, beta, w, bias))
+    M, K = x.shape
+    N = w.shape[1]
+    out = np.empty((M, N), np.float32)
+    ms = C.c_float(0)
+    check(load().vb_op_ln_linear(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(w), _ptr(bias), int(bool(gelu)), _ptr(out), M, N, K, iters,
+                                 C.byref(ms)))
     return out, (ms.value if iters > 0 else None)
 
 

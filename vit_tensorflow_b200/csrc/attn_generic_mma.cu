@@ -549,10 +549,16 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
   if (reinterpret_cast<uintptr_t>(v) % 16 != 0 || reinterpret_cast<uintptr_t>(S) % 16 != 0) return false;
   const int nkp = (nk + 15) & ~15;
   const int lds = nkp;
-  auto& cache = mix_cache();                                     // weights are immutable between attention_mix_cache_clear() calls
   const MixKey key{mix_a, mix_b, ln_gamma, ln_beta};
-  auto it = cache.find(key);
-  if (it == cache.end()) {
+  MixParams mixp;                                                // copied out under the lock (handles on other threads may clear the cache)
+  bool cached = false;
+  {
+    std::lock_guard<std::mutex> lock(global_cache_mutex());       // weights are immutable between attention_mix_cache_clear() calls
+    auto& cache = mix_cache();
+    auto it = cache.find(key);
+    if (it != cache.end()) { mixp = it->second; cached = true; }
+  }
+  if (!cached) {
     MixParams P = {};
     const size_t hh = static_cast<size_t>(heads) * heads * sizeof(float);
     VB_CUDA(cudaStreamSynchronize(s));
@@ -560,7 +566,9 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
     if (mix_b) VB_CUDA(cudaMemcpy(P.wb, mix_b, hh, cudaMemcpyDeviceToHost));
     if (ln_gamma) VB_CUDA(cudaMemcpy(P.gamma, ln_gamma, heads * sizeof(float), cudaMemcpyDeviceToHost));
     if (ln_beta) VB_CUDA(cudaMemcpy(P.beta, ln_beta, heads * sizeof(float), cudaMemcpyDeviceToHost));
-    it = cache.emplace(key, P).first;
+    mixp = P;
+    std::lock_guard<std::mutex> lock(global_cache_mutex());
+    mix_cache()[key] = P;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   {
@@ -568,6 +576,7 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
     static int configured[256] = {0};                               // per device: the attribute is device state
     int dev = 0;
     VB_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(global_cache_mutex());
     if (sc_smem > configured[dev & 255]) {
       VB_CUDA(cudaFuncSetAttribute(scores_stripe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sc_smem));
       configured[dev & 255] = sc_smem;
@@ -578,12 +587,12 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
   const long long rows = static_cast<long long>(B) * nq;
   const int js = (nkp + 31) / 32;                                // key slots of 32 per row: 7 for n = 196 / 197
   if (heads == 8) {
-    if (js <= 4) launch_mid_rows<8, 4, 1>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
-    else if (js <= 7) launch_mid_rows<8, 7, 1>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
-    else launch_mid_rows<8, 8, 1>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    if (js <= 4) launch_mid_rows<8, 4, 1>(S, mixp, nq, nk, lds, nkp, rows, variant, s);
+    else if (js <= 7) launch_mid_rows<8, 7, 1>(S, mixp, nq, nk, lds, nkp, rows, variant, s);
+    else launch_mid_rows<8, 8, 1>(S, mixp, nq, nk, lds, nkp, rows, variant, s);
   } else {
-    if (js <= 4) launch_mid_rows<16, 2, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
-    else launch_mid_rows<16, 4, 2>(S, it->second, nq, nk, lds, nkp, rows, variant, s);
+    if (js <= 4) launch_mid_rows<16, 2, 2>(S, mixp, nq, nk, lds, nkp, rows, variant, s);
+    else launch_mid_rows<16, 4, 2>(S, mixp, nq, nk, lds, nkp, rows, variant, s);
   }
   VB_CUDA(cudaGetLastError());
   const dim3 grid((nq + 63) / 64, B * heads);
@@ -605,7 +614,10 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
 
 }  // namespace
 
-void attention_mix_cache_clear() { mix_cache().clear(); }
+void attention_mix_cache_clear() {
+  std::lock_guard<std::mutex> lock(global_cache_mutex());
+  mix_cache().clear();
+}
 
 bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                            __nv_bfloat16* out, int ldo, float* S, int B, int nq, int nk, int heads, int dh, int variant,

@@ -446,6 +446,9 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   static unsigned long long seen[4] = {0, 0, 0, 0};
   if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
   AttnKey key{q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads};
+  AttnPlan plan;                                   // copied out under the lock: another thread may clear the cache meanwhile
+  {
+  std::lock_guard<std::mutex> lock(global_cache_mutex());
   auto& cache = plan_cache();
   auto it = cache.find(key);
   if (it == cache.end()) {
@@ -457,6 +460,8 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
     p.v = make_tmap_3d(v, inner, nk, B, static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(nk) * ldv * 2, DH, BKV, 1);
     p.o = make_tmap_3d(out, inner, nq, B, static_cast<uint64_t>(ldo) * 2, static_cast<uint64_t>(nq) * ldo * 2, DH, 32, 1);
     it = cache.emplace(key, p).first;
+  }
+  plan = it->second;
   }
   const int pairs = (nq + 2 * BQ - 1) / (2 * BQ);
   const int num_items = B * heads * pairs;
@@ -472,7 +477,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, it->second.q, it->second.k, it->second.v, it->second.o, heads, nq, nk,
+  VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, plan.q, plan.k, plan.v, plan.o, heads, nq, nk,
                              num_items, scale_log2, attn_trace_buffer()));
   VB_CUDA(cudaGetLastError());
   count_launch();

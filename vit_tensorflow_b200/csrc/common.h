@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 
@@ -32,7 +33,14 @@ int sm_count();
 
 // Kernel function attributes (opt-in shared memory) are per DEVICE, and one process may hold handles on several GPUs:
 // true the first time the calling site runs on the current device.
+// Thread-safe: distinct handles may be driven from distinct threads (include/vitb200.h), and every process-wide cache of
+// this library (this bitmap, sm_count, the attention TMA-plan and head-mix caches) is guarded by a mutex.
+inline std::mutex& global_cache_mutex() {
+  static std::mutex m;
+  return m;
+}
 inline bool first_use_on_this_device(unsigned long long (&seen)[4]) {
+  std::lock_guard<std::mutex> lock(global_cache_mutex());
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return true;
   unsigned long long& word = seen[(dev >> 6) & 3];
@@ -63,9 +71,12 @@ struct GemmBf16 {
   bool gelu = false;
   int grid = 0;
   // Folded LayerNorm of the A operand (Wt must hold gamma-scaled weights, bias the beta.W + b term):
-  //   out = rstd[m] * (acc - mu[m] * ln_c1[n]) + bias[n], with (mu, rstd) per row in ln_rows.
+  //   out = rstd[m] * (acc - mu[m] * ln_c1[n]) + bias[n], with (mu, rstd) of row m reduced in the epilogue from the
+  //   ln_parts (sum, sumsq) partials of that row (the stats_out format below) over 1 / ln_inv_d elements.
   const float* ln_c1 = nullptr;
-  const float* ln_rows = nullptr;       // [M, 2] = (mu, rstd)
+  const float* ln_stats = nullptr;      // [M, ln_parts, 2]
+  int ln_parts = 0;
+  float ln_inv_d = 0.f;
   // Emit (sum, sumsq) of every 64-column chunk of the stored bf16 output rows: [M, N/64, 2]
   float* stats_out = nullptr;
   int stats_parts = 0;

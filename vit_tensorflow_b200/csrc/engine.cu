@@ -98,7 +98,7 @@ struct Epi {
   const void* res = nullptr;
   int ldr = 0;
   bool gelu = false;
-  const float* ln_rows = nullptr;    // per-row (mean, rstd) of the A operand for a LayerNorm-folded Dense, [M, 2]
+  const float* ln_stats = nullptr;   // (sum, sumsq) partials per 64-column chunk of the A operand's rows for a LayerNorm-folded Dense, [M, K/64, 2]
   float* stats_out = nullptr;        // emit (sum, sumsq) partials of every 64-column chunk of the output rows, [M, N/64, 2]
 };
 
@@ -569,6 +569,9 @@ struct vb_handle {
     ResKey key{&e, B, rows};
     auto it = embed_res.find(key);
     if (it == embed_res.end()) {
+      // one entry per (embedding, batch, rows) actually in use; a server that sweeps batch / image sizes must not grow
+      // without bound (77 MB per ViT-B/16 B=256 entry): beyond a handful of shapes start over
+      if (embed_res.size() >= 6) { VB_CUDA(cudaStreamSynchronize(s)); embed_res.clear(); }
       std::unique_ptr<DevMem> m(new DevMem());
       m->ensure(static_cast<size_t>(B) * rows * e.dim * sizeof(T));
       build_embed_residual<T>(static_cast<T*>(m->p), e.pos, e.cls, e.patch.bias, B, rows, e.dim, e.cls != nullptr, s);
@@ -679,10 +682,9 @@ struct vb_handle {
     if (fold && !*stats_valid) { ensure_stats(X, dim, stats, M, s); *stats_valid = true; }
     T* Y = arena.get<T>(static_cast<size_t>(M) * dim);
     T* O = arena.get<T>(static_cast<size_t>(M) * inner);
-    float* lnrows = fold ? arena.get<float>(static_cast<size_t>(M) * 2) : nullptr;
     const T* A = X;
     Epi eq;
-    if (fold) { finalize_stats(stats, lnrows, M, dim, s); eq.ln_rows = lnrows; }
+    if (fold) eq.ln_stats = stats;
     else { VB_CHECK(!l.folded, "internal: folded layer without statistics"); ln<T>(X, l.attn_norm, Y, M, dim, s); A = Y; }
     if (l.fused_qkv) {
       T* QKV = arena.get<T>(static_cast<size_t>(M) * 3 * inner);
@@ -706,7 +708,7 @@ struct vb_handle {
       add_tokens<T>(X, O, static_cast<long long>(M) * dim, s);   // vit.py:53: identity out-projection
       if (fold) ensure_stats(X, dim, stats, M, s);
     }
-    feed_forward<T>(X, M, dim, l, Y, s, fold ? stats : nullptr, lnrows);
+    feed_forward<T>(X, M, dim, l, Y, s, fold ? stats : nullptr);
   }
   // One parallel_vit layer (parallel_vit.py:114-117): x = sum_i attn_i(LN_i(x)) + x ; x = sum_i ff_i(LN'_i(x)) + x.
   // Every branch reads the SAME x, so the sums accumulate in a second buffer through the residual epilogue of the
@@ -721,14 +723,12 @@ struct vb_handle {
     T* O = arena.get<T>(static_cast<size_t>(M) * inner);
     T* QKV = arena.get<T>(static_cast<size_t>(M) * 3 * inner);
     T* Hb = arena.get<T>(static_cast<size_t>(M) * br[0].fc1.N);
-    float* lnrows = fold ? arena.get<float>(static_cast<size_t>(M) * 2) : nullptr;
     // ---- attention branches: X -> Acc
-    if (fold) finalize_stats(stats, lnrows, M, dim, s);
     for (int i = 0; i < nbr; ++i) {
       const LayerW& l = br[i];
       const T* A = X;
       Epi eq;
-      if (fold) { eq.ln_rows = lnrows; eq.bias = l.to_qkv.ln_c2; }
+      if (fold) { eq.ln_stats = stats; eq.bias = l.to_qkv.ln_c2; }
       else { VB_CHECK(!l.folded, "internal: folded layer without statistics"); ln<T>(X, l.attn_norm, Y, M, dim, s); A = Y; }
       linear<T>(A, dim, M, l.to_qkv, QKV, 3 * inner, eq, s);
       attention<T>(QKV, 3 * inner, QKV + inner, 3 * inner, QKV + 2 * inner, 3 * inner, O, inner, B, rows, rows, l, s);
@@ -744,22 +744,17 @@ struct vb_handle {
       }
     }
     // ---- feed-forward branches: Acc -> X
-    if (fold) finalize_stats(stats, lnrows, M, dim, s);
     for (int i = 0; i < nbr; ++i) {
       const LayerW& l = br[i];
       const T* A = Acc;
       Epi e1; e1.gelu = true;
-      if (fold) { e1.ln_rows = lnrows; e1.bias = l.fc1.ln_c2; }
+      if (fold) { e1.ln_stats = stats; e1.bias = l.fc1.ln_c2; }
       else { ln<T>(Acc, l.ff_norm, Y, M, dim, s); A = Y; e1.bias = l.fc1.bias; }
       linear<T>(A, dim, M, l.fc1, Hb, l.fc1.N, e1, s);
       Epi e2; e2.bias = l.fc2.bias; e2.res = i == 0 ? Acc : X; e2.ldr = dim;
       if (fold && i == nbr - 1) e2.stats_out = stats;
       linear<T>(Hb, l.fc1.N, M, l.fc2, X, dim, e2, s);
     }
-  }
-  void finalize_stats(const float* stats, float* rows, int M, int dim, cudaStream_t s) {
-    ProfScope ps(this, PROF_LN, 0.0, 8.0 * M * (dim / 64) + 8.0 * M, s);
-    row_stats_finalize(stats, rows, M, dim / 64, dim, s);
   }
   template <typename T>
   void ensure_stats(const T* X, int dim, float* stats, int M, cudaStream_t s);
@@ -769,11 +764,11 @@ struct vb_handle {
     layernorm<T>(x, dim, n.gamma, n.beta, y, dim, M, dim, s);
   }
   template <typename T>
-  void feed_forward(T* X, int M, int dim, const LayerW& l, T* Y, cudaStream_t s, float* stats = nullptr, float* rows = nullptr) {
+  void feed_forward(T* X, int M, int dim, const LayerW& l, T* Y, cudaStream_t s, float* stats = nullptr) {
     T* Hb = arena.get<T>(static_cast<size_t>(M) * l.fc1.N);
     Epi e1; e1.gelu = true;
     const T* A = X;
-    if (stats != nullptr) { finalize_stats(stats, rows, M, dim, s); e1.ln_rows = rows; e1.bias = l.fc1.ln_c2; }
+    if (stats != nullptr) { e1.ln_stats = stats; e1.bias = l.fc1.ln_c2; }
     else { VB_CHECK(!l.folded, "internal: folded layer without statistics"); ln<T>(X, l.ff_norm, Y, M, dim, s); A = Y; e1.bias = l.fc1.bias; }
     linear<T>(A, dim, M, l.fc1, Hb, l.fc1.N, e1, s);
     Epi e2; e2.bias = l.fc2.bias; e2.scale = l.ff_scale; e2.res = X; e2.ldr = dim;
@@ -1031,7 +1026,7 @@ void vb_handle::linear<__nv_bfloat16>(const __nv_bfloat16* A, int lda, int M, co
   const __nv_bfloat16* res = static_cast<const __nv_bfloat16*>(e.res);
   const bool fast = gemm_bf16_supported(M, L.N, K, lda, L.ldw, ldc) && (res == nullptr || e.ldr % 8 == 0);
   const bool folded = L.ln_c1 != nullptr;
-  VB_CHECK(!folded || (fast && e.ln_rows != nullptr), "internal: LayerNorm-folded Dense needs the tcgen05 path and row statistics");
+  VB_CHECK(!folded || (fast && e.ln_stats != nullptr && K % 64 == 0), "internal: LayerNorm-folded Dense needs the tcgen05 path and row statistics");
   VB_CHECK(e.stats_out == nullptr || fast, "internal: row statistics requested from a non-tcgen05 GEMM");
   ProfScope ps(this, !fast ? PROF_OTHER : e.gelu ? PROF_GEMM_GELU : res ? PROF_GEMM_RES : PROF_GEMM, 2.0 * M * L.N * K,
                2.0 * (static_cast<double>(M) * K + static_cast<double>(L.N) * K + static_cast<double>(M) * L.N * (res ? 2 : 1)), s);
@@ -1042,13 +1037,14 @@ void vb_handle::linear<__nv_bfloat16>(const __nv_bfloat16* A, int lda, int M, co
                                  static_cast<uintptr_t>(L.N), static_cast<uintptr_t>(K), reinterpret_cast<uintptr_t>(e.bias),
                                  reinterpret_cast<uintptr_t>(e.scale), reinterpret_cast<uintptr_t>(res),
                                  static_cast<uintptr_t>(e.ldr), static_cast<uintptr_t>(e.gelu),
-                                 reinterpret_cast<uintptr_t>(e.ln_rows), reinterpret_cast<uintptr_t>(L.ln_c1),
+                                 reinterpret_cast<uintptr_t>(e.ln_stats), reinterpret_cast<uintptr_t>(L.ln_c1),
                                  reinterpret_cast<uintptr_t>(e.stats_out)};
     for (int i = 0; i < 16; ++i) key[i] = parts[i];
     auto it = plans.find(key);
     if (it == plans.end()) {
+      if (plans.size() > 8192) plans.clear();      // shape sweeps: bounded host memory (a plan is four 128-byte tensor maps)
       GemmBf16 g = gemm_bf16_plan(A, lda, L.Wt, L.ldw, out, ldc, M, L.N, K, e.bias, e.scale, res, e.ldr, e.gelu);
-      if (folded) { g.ln_c1 = L.ln_c1; g.ln_rows = e.ln_rows; }
+      if (folded) { g.ln_c1 = L.ln_c1; g.ln_stats = e.ln_stats; g.ln_parts = K / 64; g.ln_inv_d = 1.0f / static_cast<float>(K); }
       if (e.stats_out) { g.stats_out = e.stats_out; g.stats_parts = L.N / 64; }
       it = plans.emplace(key, g).first;
     }
@@ -1697,6 +1693,35 @@ int vb_op_layernorm(int32_t precision, const float* x, const float* gamma, const
     };
     if (precision == VB_PRECISION_FP32) run(float());
     else run(__nv_bfloat16());
+  });
+}
+
+int vb_op_ln_linear(const float* x, const float* gamma, const float* beta, const float* w, const float* bias, int32_t gelu,
+                    float* out, int32_t M, int32_t N, int32_t K, int32_t iters, float* elapsed_ms) {
+  return guarded(nullptr, [&] {
+    require_gpu();
+    VB_CHECK(x && gamma && beta && w && out && M > 0 && N > 0 && K > 0, "vb_op_ln_linear: bad arguments");
+    VB_CHECK(N % 64 == 0 && K % 64 == 0, "vb_op_ln_linear: the folded form needs N % 64 == 0 and K % 64 == 0");
+    DevMem dX, dG, dBt, dW, dWt, dB, dC, dSt, dO;
+    const __nv_bfloat16* dx = upload<__nv_bfloat16>(dX, x, static_cast<size_t>(M) * K);
+    const float* g = upload<float>(dG, gamma, K);
+    const float* bt = upload<float>(dBt, beta, K);
+    const float* dw = upload<float>(dW, w, static_cast<size_t>(K) * N);
+    const float* db = bias ? upload<float>(dB, bias, N) : nullptr;
+    dWt.ensure(static_cast<size_t>(N) * K * 2);
+    __nv_bfloat16* wt = static_cast<__nv_bfloat16*>(dWt.p);
+    pack_weight_bf16(dw, wt, K, N, K, 0, g);                       // gamma folded into the packed weight rows
+    dC.ensure(static_cast<size_t>(N) * 2 * sizeof(float));
+    float* c = static_cast<float*>(dC.p);
+    ln_fold_consts(dw, wt, K, bt, db, c, c + N, K, N, 0);
+    dSt.ensure(static_cast<size_t>(M) * (K / 64) * 2 * sizeof(float));
+    float* st = static_cast<float*>(dSt.p);
+    dO.ensure(static_cast<size_t>(M) * N * 2);
+    __nv_bfloat16* dout = static_cast<__nv_bfloat16*>(dO.p);
+    GemmBf16 gm = gemm_bf16_plan(dx, K, wt, K, dout, N, M, N, K, c + N, nullptr, nullptr, 0, gelu != 0);
+    gm.ln_c1 = c; gm.ln_stats = st; gm.ln_parts = K / 64; gm.ln_inv_d = 1.0f / static_cast<float>(K);
+    timed(iters, elapsed_ms, [&] { row_stats_bf16(dx, K, st, M, K, 0); gemm_bf16_run(gm, 0); });
+    download<__nv_bfloat16>(dout, out, static_cast<size_t>(M) * N);
   });
 }
 

@@ -89,8 +89,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
-                 const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* __restrict__ ln_rows,
-                 float2* __restrict__ stats_out, int stats_parts, long long* __restrict__ dbg) {
+                 const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* ln_stats, int ln_parts,
+                 float ln_inv_d, float2* __restrict__ stats_out, int stats_parts, long long* __restrict__ dbg) {
   using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -251,10 +251,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t rph = 0;                                              // bit p = mbarrier phase of slab p's residual barrier
     // folded LayerNorm of the A operand: y = rstd * acc + (-rstd * mu) * c1[n] + c2[n]   (c2 arrives through `bias`);
     // (mu, rstd) of this thread's row, prefetched one tile ahead
+    // The statistics arrive as the `ln_parts` (sum, sumsq) partials per row that the producing residual GEMM's epilogue (or
+    // row_stats_bf16) emitted, one per 64-column chunk; they are reduced here in a fixed order (the former
+    // row_stats_finalize_kernel, 24 launches per ViT-B/16 forward, folded into its only consumer).  ln_stats may be the
+    // buffer a LATER kernel of the stream overwrites, never this one (stats_out of a folded GEMM is a different row set).
+    auto ln_load = [&](int r) -> float2 {
+      const float2* p = ln_stats + static_cast<size_t>(r) * ln_parts;
+      float s1 = 0.f, s2 = 0.f;
+      for (int i = 0; i < ln_parts; ++i) { const float2 v = __ldg(p + i); s1 += v.x; s2 += v.y; }
+      const float mu = s1 * ln_inv_d;
+      return make_float2(mu, rsqrtf(fmaxf(s2 * ln_inv_d - mu * mu, 0.f) + 1e-3f));
+    };
     float2 ln_next = make_float2(0.f, 1.f);
     if (EPI == 2 && tile0 < num_tiles) {
       const int r0 = (tile0 / tiles_n) * TM + cta_rank * BM + row_local;
-      if (r0 < M) ln_next = ln_rows[r0];
+      if (r0 < M) ln_next = ln_load(r0);
     }
     // Residual tiles come in through TMA (32 rows x 64 columns into the slab that will also stage the output), one
     // chunk ahead of the math.  Per-thread row reads (32 distinct 128-byte lines per LDG) saturated the LSU: clock64
@@ -288,7 +299,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         ln_nmr2 = splat2(-ln_next.x * ln_next.y);
         if (EPI == 2 && t + tile_step < num_tiles) {
           const int rn = ((t + tile_step) / tiles_n) * TM + cta_rank * BM + row_local;
-          if (rn < M) ln_next = ln_rows[rn];
+          if (rn < M) ln_next = ln_load(rn);
         }
         if (lane == 0 && q == 0) trace(1 + j, 10);
         mbar_wait(tfull_bar(acc), static_cast<uint32_t>(it >> 1) & 1u);
@@ -434,14 +445,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
+  static const EncodeTiledFn fn = [] {             // C++11 magic static: initialised once, thread-safe
     void* p = nullptr;
     cudaDriverEntryPointQueryResult qres;
     VB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
     VB_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
   return fn;
 }
 
@@ -472,7 +482,8 @@ void launch(const GemmBf16& g, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.tmap_r, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
-                             reinterpret_cast<const float2*>(g.ln_rows), reinterpret_cast<float2*>(g.stats_out), g.stats_parts, gemm_trace_buffer()));
+                             reinterpret_cast<const float2*>(g.ln_stats), g.ln_parts, g.ln_inv_d, reinterpret_cast<float2*>(g.stats_out),
+                             g.stats_parts, gemm_trace_buffer()));
   count_launch();
 }
 
@@ -480,7 +491,7 @@ template <int BN, int CG>
 void launch_epi(const GemmBf16& g, cudaStream_t stream) {
   const bool res = g.res != nullptr;
   const int epi = g.ln_c1 != nullptr ? 2 : g.bias != nullptr ? 1 : 0;
-  VB_CHECK(epi != 2 || (g.bias != nullptr && g.ln_rows != nullptr), "folded LayerNorm needs c1, c2 and the row statistics");
+  VB_CHECK(epi != 2 || (g.bias != nullptr && g.ln_stats != nullptr && g.ln_parts > 0), "folded LayerNorm needs c1, c2 and the row statistics");
 #define VB_GEMM_CASE(G, R, E) if (g.gelu == G && res == R && epi == E) return launch<BN, G, R, CG, E>(g, stream)
   VB_GEMM_CASE(false, false, 0); VB_GEMM_CASE(false, false, 1); VB_GEMM_CASE(false, false, 2);
   VB_GEMM_CASE(true, false, 0);  VB_GEMM_CASE(true, false, 1);  VB_GEMM_CASE(true, false, 2);
@@ -491,14 +502,14 @@ void launch_epi(const GemmBf16& g, cudaStream_t stream) {
 
 }  // namespace
 
-int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    VB_CUDA(cudaGetDevice(&dev));
-    VB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return n;
+int sm_count() {                                  // of the CURRENT device (one process may hold handles on several GPUs)
+  static int n[64] = {0};
+  int dev = 0;
+  VB_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(global_cache_mutex());
+  int& v = n[dev & 63];
+  if (v == 0) VB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+  return v;
 }
 
 CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes, uint32_t box_inner,

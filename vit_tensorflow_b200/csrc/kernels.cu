@@ -610,7 +610,8 @@ void count_launch(int n) { g_launches.fetch_add(n); }
 template <typename T>
 void im2col(const float* img, T* out, int B, int H, int W, int C, int ph, int pw, int cls_row, int ldo, cudaStream_t s) {
   const int rows = cls_row + (H / ph) * (W / pw);
-  const bool vec = ((pw * C) % 4 == 0) && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(img) % 16 == 0);
+  const bool vec = ((pw * C) % 4 == 0) && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(img) % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(out) % (4 * sizeof(T)) == 0);
   if (vec) {
     const long long total = static_cast<long long>(B) * rows * (ldo / 4);
     im2col_kernel<T, true><<<grid_1d(total), 256, 0, s>>>(img, out, B, H, W, C, ph, pw, cls_row, ldo);

@@ -39,24 +39,6 @@ def _layerscale_eps(depth):  # cait.py:36-41
     return 1e-6
 
 
-class _Tensorish:
-    """Tiny attribute carrier so wrappers can read `model.pos_embedding.shape` (mae.py:33)."""
-
-    def __init__(self, model, name):
-        self._m, self._n = model, name
-
-    @property
-    def shape(self):
-        return self._m.get_weight(self._n).shape
-
-    def numpy(self):
-        return self._m.get_weight(self._n)
-
-    def __array__(self, dtype=None, copy=None):
-        a = self._m.get_weight(self._n)
-        return a.astype(dtype) if dtype is not None else a
-
-
 class _Transformer:
     """`model.transformer(tokens)` (vit.py:99-104): the entry the reference's wrappers call with any n."""
 
@@ -162,6 +144,25 @@ class _EngineModel:
     def get_weight(self, name):
         return self._weights[name]
 
+    # `model.pos_embedding` / `model.cls_token` as the reference's wrappers use them: `.shape` (mae.py:33), slicing
+    # `encoder.pos_embedding[:, 1:(n + 1)]` (mae.py:54, simmim.py:95), `pos_embedding[:, :(n + 1)]` (mpp.py:208), einops
+    # `repeat(transformer.cls_token, ...)` (mpp.py:204) and arithmetic with token arrays: the float32 numpy array the model
+    # currently holds for that weight (read-only view; assign through set_weights_dict).
+    def _weight_view(self, name):
+        if name not in self._specs:
+            raise AttributeError(f"{type(self).__name__} has no weight '{name}'")
+        a = self._weights[name].view()
+        a.flags.writeable = False
+        return a
+
+    @property
+    def pos_embedding(self):
+        return self._weight_view("pos_embedding")
+
+    @property
+    def cls_token(self):
+        return self._weight_view("cls_token")
+
     def load_weights(self, path):
         with np.load(path) as z:
             self.set_weights_dict({k: z[k] for k in z.files})
@@ -206,6 +207,8 @@ class _EngineModel:
     def forward_tokens(self, tokens):
         self._finalize()
         x = np.ascontiguousarray(tokens, dtype=np.float32)
+        if x.ndim != 3 or x.shape[2] != self._cfg.dim:
+            raise ValueError(f"transformer(tokens): expected [batch, n, {self._cfg.dim}] tokens, got {x.shape}")
         b, n, _ = x.shape
         out = np.empty_like(x)
         _lib.check(self._lib.vb_forward_tokens(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, n,
@@ -282,9 +285,6 @@ class _EngineModel:
         """The attribute surface the reference's wrappers use: patch_embedding(.layers), pos_embedding,
         cls_token, dropout, mlp_head."""
         self.patch_embedding = _PatchEmbedding(self)
-        self.pos_embedding = _Tensorish(self, "pos_embedding")
-        if "cls_token" in self._specs:
-            self.cls_token = _Tensorish(self, "cls_token")
         self.dropout = _Layer(lambda x: x)               # inference semantics: identity (vit.py:148,166)
         self.mlp_head = _Layer(self.forward_head)
 

@@ -146,7 +146,11 @@ class HostPipeline:
         self.d2h_bytes = self.out_host[0].numel() * 4
 
     def submit(self, img_host):
-        """img_host: pinned float32 NHWC CPU tensor [B,h,w,3].  Returns host logits of the previous submit (or None)."""
+        """img_host: pinned float32 NHWC CPU tensor [B,h,w,3].  Returns host logits of the previous submit (or None).
+
+        Buffer lifetime: the returned tensor is one of TWO pinned staging buffers; the NEXT call to `submit` queues the
+        device-to-host copy that overwrites it (asynchronously), so consume or copy it before calling `submit` again.
+        `img_host` may be refilled once the following `submit` has returned (its H2D copy has completed by then)."""
         import torch
         k = self.i & 1
         with torch.cuda.stream(self.copy_stream):
