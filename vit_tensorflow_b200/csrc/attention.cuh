@@ -13,10 +13,12 @@ void attention_generic(const T* q, int ldq, const T* k, int ldk, const T* v, int
                        int nk, int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* ln_gamma,
                        const float* ln_beta, cudaStream_t s);
 
+// scale: softmax scale; <= 0 means dh^-0.5 (vit.py:57).  A layer whose heads were zero-padded to the kernels' head width
+// (engine.cu: dh 48 -> 64) passes its true dim_head^-0.5 here.
 template <typename T>
 bool attention_fast(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq, int nk,
                     int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* ln_gamma,
-                    const float* ln_beta, cudaStream_t s);
+                    const float* ln_beta, cudaStream_t s, float scale = 0.f);
 
 // The talking-heads / re-attention path keeps host copies of the head-mix weights keyed by their device pointers; whoever
 // frees or rewrites such weights (vb_finalize, vb_destroy, the op-level test entry) must drop them.
@@ -26,6 +28,12 @@ void attention_mix_cache_clear();
 bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                            __nv_bfloat16* out, int ldo, float* S, int B, int nq, int nk, int heads, int dh, int variant,
                            const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta, cudaStream_t s);
+
+// One-kernel attention for a single query row per image (CaiT class attention, CrossViT cross attention; any variant):
+// attn_cls.cu.  false if the shape is not covered.
+bool attention_cls(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                   __nv_bfloat16* out, int ldo, int B, int nk, int heads, int dh, int variant, const float* mix_a,
+                   const float* mix_b, const float* ln_gamma, const float* ln_beta, cudaStream_t s, float scale = 0.f);
 
 long long*& attn_trace_buffer();   // debugging aid: device trace buffer of the tcgen05 attention kernel (null = off)
 

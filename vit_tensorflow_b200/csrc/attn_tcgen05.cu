@@ -438,8 +438,10 @@ std::map<AttnKey, AttnPlan>& plan_cache() {
 template <>
 bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
                                    __nv_bfloat16* out, int ldo, int B, int nq, int nk, int heads, int dh, int variant,
-                                   const float*, const float*, const float*, const float*, cudaStream_t s) {
-  if (variant != 0 || dh != DH || nq < 16) return false;   // head-mixing variants and 1-row queries: generic path
+                                   const float* mix_a, const float* mix_b, const float* ln_g, const float* ln_b, cudaStream_t s,
+                                   float scale) {
+  if (nq == 1 && attention_cls(q, ldq, k, ldk, v, ldv, out, ldo, B, nk, heads, dh, variant, mix_a, mix_b, ln_g, ln_b, s, scale)) return true;
+  if (variant != 0 || dh != DH || nq < 2) return false;    // head-mixing variants: attn_mix path / generic path
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
        reinterpret_cast<uintptr_t>(out)) % 16) return false;
@@ -466,7 +468,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   const int pairs = (nq + 2 * BQ - 1) / (2 * BQ);
   const int num_items = B * heads * pairs;
   const int grid = num_items < sm_count() ? num_items : sm_count();
-  const float scale_log2 = (1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
+  const float scale_log2 = (scale > 0.f ? scale : 1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(ATT_THREADS);

@@ -111,7 +111,8 @@ struct LayerW {                    // one pre-norm transformer layer in any of t
   Norm reattn_norm;                // DeepViT
   const float* attn_scale = nullptr;  // CaiT LayerScale
   const float* ff_scale = nullptr;
-  int heads = 0, dim_head = 0, variant = 0;
+  int heads = 0, dim_head = 0, variant = 0;   // dim_head: head width of the q/k/v ACTIVATIONS (the padded width when dh_model < it)
+  int dh_model = 0;                  // the model's dim_head: softmax scale dh_model^-0.5 (vit.py:57)
   bool folded = false;               // attn_norm / ff_norm folded into to_qkv (to_q, to_kv) / fc1
 };
 
@@ -245,6 +246,23 @@ struct vb_handle {
   using PlanKey = std::array<uintptr_t, 16>;
   std::map<PlanKey, GemmBf16> plans;
 
+  // Whole-forward CUDA graphs (vb_forward): the launch sequence of one (image pointer, logits pointer, batch, h, w, stream)
+  // combination is captured on its SECOND call (the first runs eagerly and does every lazy host-side step: arena growth,
+  // kernel attributes, descriptor / residual caches) and replayed from the third on.  Workspace pointers are stable (the
+  // arena is reset, never freed, per forward), so a replay touches exactly the memory the eager run would.  Programmatic
+  // dependent launches are captured as programmatic edges.  VB_NO_GRAPH=1 disables it; profiling and the legacy default
+  // stream (which cannot be captured) always run eagerly.
+  struct GraphKey {
+    const void* img; void* out; int B, H, W; cudaStream_t s;
+    bool operator<(const GraphKey& o) const { return std::tie(img, out, B, H, W, s) < std::tie(o.img, o.out, o.B, o.H, o.W, o.s); }
+  };
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int calls = 0; long long launches = 0; bool failed = false; };
+  std::map<GraphKey, GraphEntry> graphs;
+  void drop_graphs() {
+    for (auto& g : graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    graphs.clear();
+  }
+
   bool bf16() const { return cfg.precision == VB_PRECISION_BF16; }
 
   // ---------------------------------------------------------------- weight registry
@@ -370,7 +388,11 @@ struct vb_handle {
     }
   }
 
+  // finalize-time replacements of registered weights by derived device copies (head-padded kernels)
+  std::map<std::string, const float*> woverride;
   const float* W(const std::string& name) const {
+    auto ov = woverride.find(name);
+    if (ov != woverride.end()) return ov->second;
     auto it = windex.find(name);
     VB_CHECK(it != windex.end(), "internal: unknown weight " + name);
     return weights[it->second].dev;
@@ -430,6 +452,27 @@ struct vb_handle {
   // fold_ok: the layer is only ever used as a self-attention layer (its LayerNorms feed nothing but GEMMs)
   LayerW make_layer(const std::string& pre, int dim, int heads, int dh, int mlp, int kind, bool fold_ok = true) {
     LayerW l;
+    l.dh_model = dh;
+    // Plain softmax attention with dim_head < 64 (bf16 engine): widen every head to the tcgen05 attention kernel's 64 columns
+    // with zero weights -- extra to_qkv / to_q / to_kv output columns (q, k, v pad columns are exactly 0, so QK^T and the
+    // real PV columns are unchanged) and zero to_out input rows.  Costs (64 / dh - 1) more flops in those two GEMMs and buys
+    // the tensor-core attention path for e.g. dim_head 48 / 32 (the head-mixing variants have their own kernel, attn_mix).
+    const bool to_out_present = has(pre + "to_out.kernel");
+    if (bf16() && dh < 64 && dh % 8 == 0 && to_out_present && dim % 8 == 0 && getenv("VB_NO_HEAD_PAD") == nullptr &&
+        (kind == VB_KIND_VIT || kind == VB_KIND_CROSSVIT)) {
+      const int dhp = 64;
+      auto padded = [&](const std::string& n, int other, int groups, int pad_rows) {
+        owned.emplace_back(new DevMem());
+        owned.back()->ensure(static_cast<size_t>(other) * groups * heads * dhp * sizeof(float));
+        float* wp = static_cast<float*>(owned.back()->p);
+        pad_heads_f32(W(n), wp, other, groups, heads, dh, dhp, pad_rows, 0);
+        woverride[n] = wp;
+      };
+      if (kind == VB_KIND_VIT) padded(pre + "to_qkv.kernel", dim, 3, 0);
+      else { padded(pre + "to_q.kernel", dim, 1, 0); padded(pre + "to_kv.kernel", dim, 2, 0); }
+      padded(pre + "to_out.kernel", dim, 1, 1);
+      dh = dhp;
+    }
     const int inner = heads * dh;
     l.heads = heads; l.dim_head = dh;
     l.attn_norm = make_norm(pre + "attn_norm", dim);
@@ -467,6 +510,8 @@ struct vb_handle {
     for (auto& w : weights) VB_CHECK(w.set, "vb_finalize: weight '" + w.name + "' was never set");
     VB_CUDA(cudaSetDevice(device));
     owned.clear(); layers.clear(); cls_layers.clear(); t2t_layers.clear(); xblocks.clear(); plans.clear(); embed_res.clear();
+    woverride.clear();
+    drop_graphs();
     const vb_config& c = cfg;
     if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT || c.kind == VB_KIND_PARALLEL_VIT) {
       const int np = (c.image_h / c.patch_h) * (c.image_w / c.patch_w);
@@ -556,13 +601,14 @@ struct vb_handle {
   template <typename T>
   void attention(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq, int nk,
                  const LayerW& l, cudaStream_t s) {
+    const float scale = l.dh_model != l.dim_head ? 1.0f / sqrtf(static_cast<float>(l.dh_model)) : 0.f;
     attention_dispatch<T>(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, l.heads, l.dim_head, l.variant, l.mix_a, l.mix_b,
-                          l.reattn_norm.gamma, l.reattn_norm.beta, s);
+                          l.reattn_norm.gamma, l.reattn_norm.beta, s, scale);
   }
   template <typename T>
   void attention_dispatch(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq, int nk,
                           int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* g, const float* b,
-                          cudaStream_t s);
+                          cudaStream_t s, float scale = 0.f);
 
   template <typename T>
   const T* embed_residual(const EmbedW& e, int B, int rows, cudaStream_t s) {
@@ -571,7 +617,7 @@ struct vb_handle {
     if (it == embed_res.end()) {
       // one entry per (embedding, batch, rows) actually in use; a server that sweeps batch / image sizes must not grow
       // without bound (77 MB per ViT-B/16 B=256 entry): beyond a handful of shapes start over
-      if (embed_res.size() >= 6) { VB_CUDA(cudaStreamSynchronize(s)); embed_res.clear(); }
+      if (embed_res.size() >= 6) { VB_CUDA(cudaStreamSynchronize(s)); embed_res.clear(); drop_graphs(); }
       std::unique_ptr<DevMem> m(new DevMem());
       m->ensure(static_cast<size_t>(B) * rows * e.dim * sizeof(T));
       build_embed_residual<T>(static_cast<T*>(m->p), e.pos, e.cls, e.patch.bias, B, rows, e.dim, e.cls != nullptr, s);
@@ -1066,10 +1112,11 @@ void vb_handle::ensure_stats<__nv_bfloat16>(const __nv_bfloat16* X, int dim, flo
 template <typename T>
 void vb_handle::attention_dispatch(const T* q, int ldq, const T* k, int ldk, const T* v, int ldv, T* out, int ldo, int B, int nq,
                                    int nk, int heads, int dh, int variant, const float* mix_a, const float* mix_b, const float* g,
-                                   const float* b, cudaStream_t s) {
+                                   const float* b, cudaStream_t s, float scale) {
   ProfScope ps(this, PROF_ATTN, 4.0 * B * heads * nq * nk * dh + (variant == 1 ? 2.0 : variant == 2 ? 4.0 : 0.0) * B * nq * nk * heads * heads,
                static_cast<double>(sizeof(T)) * B * heads * dh * (2.0 * nq + 2.0 * nk), s);
-  if (attention_fast<T>(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s)) return;
+  if (attention_fast<T>(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s, scale)) return;
+  VB_CHECK(scale <= 0.f, "internal: a head-padded layer must run on the tcgen05 attention kernel");
   float* S = arena.get<float>(static_cast<size_t>(B) * heads * nq * ((nk + 15) & ~15));   // row pitch padded for the bf16-P path
   attention_generic<T>(q, ldq, k, ldk, v, ldv, out, ldo, S, B, nq, nk, heads, dh, variant, mix_a, mix_b, g, b, s);
 }
@@ -1309,8 +1356,46 @@ int vb_forward(vb_handle* h, const float* img, int32_t img_mem, int32_t batch, i
       h->logits_dev.ensure(out_bytes);
       out_d = static_cast<float*>(h->logits_dev.p);
     }
-    if (h->bf16()) h->forward_impl<__nv_bfloat16>(img_d, batch, img_h, img_w, out_d, s);
-    else h->forward_impl<float>(img_d, batch, img_h, img_w, out_d, s);
+    auto run_eager = [&] {
+      if (h->bf16()) h->forward_impl<__nv_bfloat16>(img_d, batch, img_h, img_w, out_d, s);
+      else h->forward_impl<float>(img_d, batch, img_h, img_w, out_d, s);
+    };
+    static const bool graphs_off = getenv("VB_NO_GRAPH") != nullptr;
+    const bool graphable = !graphs_off && !h->profiling && s != nullptr && s != cudaStreamLegacy;
+    bool done = false;
+    if (graphable) {
+      if (h->graphs.size() > 64) h->drop_graphs();                         // shape / pointer sweeps: bounded
+      vb_handle::GraphEntry& ge = h->graphs[vb_handle::GraphKey{img_d, out_d, batch, img_h, img_w, s}];
+      ++ge.calls;
+      if (ge.exec != nullptr) {
+        VB_CUDA(cudaGraphLaunch(ge.exec, s));
+        count_launch(static_cast<int>(ge.launches));
+        done = true;
+      } else if (ge.calls == 2 && !ge.failed) {
+        cudaGraph_t graph = nullptr;
+        const long long l0 = launch_counter();
+        if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+          bool ok = true;
+          std::string why;
+          try { run_eager(); } catch (const std::exception& e) { ok = false; why = e.what(); }
+          const cudaError_t ec = cudaStreamEndCapture(s, &graph);
+          if (ok && ec == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess) {
+            ge.launches = launch_counter() - l0;
+            VB_CUDA(cudaGraphLaunch(ge.exec, s));
+            done = true;
+          } else {
+            ge.failed = true;                                               // stay eager for this key
+            ge.exec = nullptr;
+            cudaGetLastError();
+          }
+          if (graph != nullptr) cudaGraphDestroy(graph);
+        } else {
+          ge.failed = true;
+          cudaGetLastError();
+        }
+      }
+    }
+    if (!done) run_eager();
     h->last_launches = launch_counter() - before;
     if (logits_mem == VB_MEM_HOST) {
       VB_CUDA(cudaMemcpyAsync(logits, out_d, out_bytes, cudaMemcpyDeviceToHost, s));
@@ -1537,6 +1622,7 @@ void vb_destroy(vb_handle* h) {
   cudaSetDevice(h->device);
   if (h->dp_comm != nullptr) { nccl().CommDestroy(h->dp_comm); h->dp_comm = nullptr; }
   attention_mix_cache_clear();
+  h->drop_graphs();
   for (auto& w : h->weights) if (w.dev) cudaFree(w.dev);
   h->prof_collect();
   for (auto e : h->event_pool) cudaEventDestroy(e);

@@ -590,6 +590,21 @@ __global__ void row_stats_finalize_kernel(const float2* __restrict__ stats, floa
   rows[m] = make_float2(mu, rsqrtf(fmaxf(s2 * inv_d - mu * mu, 0.f) + 1e-3f));
 }
 
+__global__ void pad_heads_kernel(const float* __restrict__ W, float* __restrict__ Wp, int other, int groups, int heads, int dh, int dhp,
+                                 int pad_rows) {
+  const long long total = static_cast<long long>(other) * groups * heads * dhp;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int wide = groups * heads * dhp, narrow = groups * heads * dh;
+    long long o; int c;                              // o: index along the untouched dimension, c: padded (g, h, d) index
+    if (pad_rows) { c = static_cast<int>(idx / other); o = idx % other; } else { o = idx / wide; c = static_cast<int>(idx % wide); }
+    const int d = c % dhp, gh = c / dhp;
+    float v = 0.f;
+    if (d < dh) v = pad_rows ? W[static_cast<long long>(gh * dh + d) * other + o] : W[o * narrow + gh * dh + d];
+    Wp[idx] = v;
+  }
+}
+
 inline int grid_1d(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = static_cast<long long>(sm_count()) * 16;
@@ -619,6 +634,12 @@ void im2col(const float* img, T* out, int B, int H, int W, int C, int ph, int pw
     const long long total = static_cast<long long>(B) * rows * ldo;
     im2col_kernel<T, false><<<grid_1d(total), 256, 0, s>>>(img, out, B, H, W, C, ph, pw, cls_row, ldo);
   }
+  VB_LAUNCHED();
+}
+
+void pad_heads_f32(const float* W, float* Wp, int other, int groups, int heads, int dh, int dhp, int pad_rows, cudaStream_t s) {
+  const long long total = static_cast<long long>(other) * groups * heads * dhp;
+  pad_heads_kernel<<<grid_1d(total), 256, 0, s>>>(W, Wp, other, groups, heads, dh, dhp, pad_rows);
   VB_LAUNCHED();
 }
 

@@ -71,6 +71,11 @@ void add_inplace_f32(float* a, const float* b, long long count, cudaStream_t s);
 // Wt[n*ldw + k] = bf16(W[k*N + n]) : Keras [K,N] fp32 -> K-major bf16 rows (zero padded to ldw)
 // row_scale (may be null): Wt[n*ldw + k] = bf16(W[k*N + n] * row_scale[k])  (LayerNorm gamma folded into the weight)
 void pack_weight_bf16(const float* W, __nv_bfloat16* Wt, int K, int N, int ldw, cudaStream_t s, const float* row_scale = nullptr);
+// Head-padded copy of a Dense kernel (fp32, Keras [K, N] layout) for layers whose dim_head is widened to the attention
+// kernel's head width with zero weights.  pad_rows == 0: the N = groups*heads*dh output columns [g][h][d] become
+// groups*heads*dhp columns, column (g, h, d >= dh) = 0 (to_qkv: groups 3, to_q: 1, to_kv: 2).  pad_rows == 1: the
+// K = heads*dh input rows become heads*dhp rows, row (h, d >= dh) = 0 (to_out).  `other` is the untouched dimension.
+void pad_heads_f32(const float* W, float* Wp, int other, int groups, int heads, int dh, int dhp, int pad_rows, cudaStream_t s);
 // Constants of a LayerNorm folded into the following Dense (see gemm_tcgen05.cu):
 //   c1[n] = sum_k float(Wt[n,k])   (the gamma-scaled, bf16-rounded weights the tensor core really multiplies)
 //   c2[n] = sum_k beta[k] * W[k,n] + (bias ? bias[n] : 0)
