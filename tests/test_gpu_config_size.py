@@ -32,12 +32,12 @@ FULL = {
 
 # |err| <= ATOL + RTOL * |ref| on logits of standard deviation ~1 (|ref| max 2.6 - 4.3).  Measured maxima on the B200 are in
 # the comment of each line; the bound is <= 3x that.
-TOL = {
-    "c2_vit_b16_224": (3.0e-2, 1.0e-2),
-    "c3_deepvit_1024x24": (6.0e-2, 2.0e-2),
-    "c4_cait_s36_dh48": (3.0e-2, 1.0e-2),
-    "c4_cait_s36_dh64": (3.0e-2, 1.0e-2),
-    "c5_vit_l16_384": (4.5e-2, 1.5e-2),
+TOL = {   # (atol, rtol); measured max |err| on the B200, round 2 (gpurun_out/config_size_parity.json -> DESIGN.md section 6):
+    "c2_vit_b16_224": (4.0e-2, 1.0e-2),        # 0.026 (stress) / 0.030 (init), |ref| <= 3.9
+    "c3_deepvit_1024x24": (6.0e-2, 2.0e-2),    # 0.038 / 0.044, |ref| <= 3.7
+    "c4_cait_s36_dh48": (7.0e-2, 2.0e-2),      # 0.050 / 0.023 (38 layers, O(1) LayerScale in the stress set), |ref| <= 2.8
+    "c4_cait_s36_dh64": (6.0e-2, 2.0e-2),      # 0.042 / 0.022
+    "c5_vit_l16_384": (6.0e-2, 1.5e-2),        # 0.036 / 0.041, |ref| <= 4.3
 }
 
 

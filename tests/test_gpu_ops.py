@@ -191,7 +191,7 @@ def test_attention_lazy_rescale(lib, B, n, heads, ramp):
     if ramp != "down":
         assert crossed.any(-1).mean() > 0.9, "test construction: the ramp does not trigger the lazy rescale"
     else:
-        assert not crossed.any()
+        assert crossed.any(-1).mean() < 0.2      # a few rows whose first block happens to score low still cross
     _assert_close_sigma(out, ref, 1.5e-2, 1.0e-2)
 
 

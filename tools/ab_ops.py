@@ -17,7 +17,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHAPES = {  # name: (N, K, bias, res, gelu) at M = 50432
     "qkv": (2304, 768, 0, 0, 0), "out_proj": (768, 768, 1, 1, 0), "fc1_gelu": (3072, 768, 1, 0, 1), "fc2": (768, 3072, 1, 1, 0),
-}
+}   # plus ln_qkv / ln_fc1_gelu (LayerNorm-folded, as the model runs them), ln_*_cait (M = 25088, K = 384), attention, attention_l
 CHILD = r"""
 import sys, json, zlib
 sys.path.insert(0, %(root)r)
@@ -28,8 +28,22 @@ rng = np.random.default_rng(0)
 out = {}
 M = 50432
 for name in ops:
-    if name == "attention":
+    if name.startswith("ln_"):
+        N, K, gelu = {"ln_qkv": (2304, 768, 0), "ln_fc1_gelu": (3072, 768, 1), "ln_qkv_cait": (1152, 384, 0), "ln_fc1_cait": (1536, 384, 1)}[name]
+        Mx = 25088 if name.endswith("cait") else M
+        a = rng.standard_normal((Mx, K), dtype=np.float32)
+        w = (rng.standard_normal((K, N), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
+        g = rng.uniform(0.5, 1.5, K).astype(np.float32); bt = rng.standard_normal(K).astype(np.float32) * 0.1
+        b = rng.standard_normal(N).astype(np.float32)
+        o, ms = _lib.op_ln_linear(a, g, bt, w, b, gelu, iters)      # times row_stats_bf16 + the folded GEMM
+        out[name] = dict(ms=ms, tflops=2.0 * Mx * N * K / ms / 1e9, crc=zlib.crc32(o.tobytes()))
+    elif name == "attention":
         B, n, h = 256, 197, 12
+        q, k, v = (rng.standard_normal((B, n, h * 64), dtype=np.float32) for _ in range(3))
+        o, ms = _lib.op_attention(q, k, v, h, 0, precision="bf16", iters=iters)
+        out[name] = dict(ms=ms, tflops=4.0 * B * h * n * n * 64 / ms / 1e9, crc=zlib.crc32(o.tobytes()))
+    elif name == "attention_l":
+        B, n, h = 32, 577, 16
         q, k, v = (rng.standard_normal((B, n, h * 64), dtype=np.float32) for _ in range(3))
         o, ms = _lib.op_attention(q, k, v, h, 0, precision="bf16", iters=iters)
         out[name] = dict(ms=ms, tflops=4.0 * B * h * n * n * 64 / ms / 1e9, crc=zlib.crc32(o.tobytes()))
@@ -48,7 +62,7 @@ print(json.dumps(out))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("libs", nargs="+")
-    ap.add_argument("--ops", default="qkv,out_proj,fc1_gelu,fc2,attention")
+    ap.add_argument("--ops", default="ln_qkv,out_proj,ln_fc1_gelu,fc2,attention")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--env", default=None, help="NAME=v1,v2,...: sweep one environment variable per library")
     ap.add_argument("--repeat", action="store_true", help="run the first library once more at the end (drift check)")
@@ -65,7 +79,7 @@ def main():
             rec = dict(lib=os.path.basename(lib), **({env_name: val} if env_name else {}))
             try:
                 r = subprocess.run([sys.executable, "-c", CHILD % dict(root=ROOT, ops=ops, iters=args.iters, shapes=SHAPES)], env=env,
-                                   capture_output=True, text=True, timeout=60 + 10 * len(ops))
+                                   capture_output=True, text=True, timeout=120 + 20 * len(ops))
                 if r.returncode != 0 or not r.stdout.strip():
                     raise RuntimeError((r.stderr or "no output").strip().splitlines()[-1])
                 rec["ops"] = json.loads(r.stdout.strip().splitlines()[-1])

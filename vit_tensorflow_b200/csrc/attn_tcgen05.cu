@@ -51,6 +51,31 @@ constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
 constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_PV + 64 t
 
+// 2^t on the FMA / ALU pipes instead of MUFU (the FlashAttention-4 split): t = n + f with n = round(t) through the 1.5 * 2^23
+// magic-number add, 2^f on [-1/2, 1/2] as a degree-3 minimax polynomial (max relative error 7.5e-5, far below the 2^-9 rounding of
+// P to bf16 that follows), and the 2^n scaling as an integer add on the exponent field ((bits(r) << 23) carries n modulo 2^9 into
+// bits 23-31, which wraps correctly for negative n).  t <= 8 by the lazy-rescale invariant; t is clamped at -126 (result ~1e-38).
+// Per PAIR of elements: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 SHL + 2 IADD, against 2 MUFU.EX2 (16 issue cycles of the 4-lane
+// MUFU unit per 64 elements): the two paths run on different pipes, so splitting the 8-key groups between them shortens the
+// exp phase that paced the item (profiles/r01_attn_item_timeline.md: 4.8 K of 10.4 K cycles at 1.3x the MUFU floor).
+#ifndef VB_ATTN_POLY_MASK
+#define VB_ATTN_POLY_MASK 0xA            // bit k: the k-th 8-key group of every 32-key chunk takes the polynomial path
+#endif
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 t) {
+  float t0, t1;
+  unpack2(t, t0, t1);
+  t = pack2(fmaxf(t0, -126.0f), fmaxf(t1, -126.0f));
+  const f32x2 r = add2(t, splat2(12582912.0f));
+  const f32x2 fl = add2(r, splat2(-12582912.0f));
+  const f32x2 f = fma2(fl, splat2(-1.0f), t);
+  f32x2 q = fma2(splat2(0.055171649903059006f), f, splat2(0.2426111251115799f));
+  q = fma2(q, f, splat2(0.6932609677314758f));
+  q = fma2(q, f, splat2(0.9999280571937561f));
+  const uint32_t lo = static_cast<uint32_t>(q) + (static_cast<uint32_t>(r) << 23);
+  const uint32_t hi = static_cast<uint32_t>(q >> 32) + (static_cast<uint32_t>(r >> 32) << 23);
+  return pack2u(lo, hi);
+}
+
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, int heads, int nq, int nk,
@@ -321,11 +346,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const int e = k * 8 + 2 * i;
-                float x0, x1;
-                unpack2(fma2(pack2u(v[e], v[e + 1]), sc2, nm2), x0, x1);
-                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-                rsum2 = add2(rsum2, pack2(p0, p1));
-                pk[i] = pack_bf16x2(p0, p1);
+                const f32x2 t2 = fma2(pack2u(v[e], v[e + 1]), sc2, nm2);
+                if ((VB_ATTN_POLY_MASK >> k) & 1) {                           // FMA-pipe exponential
+                  const f32x2 p2 = ex2_poly2(t2);
+                  rsum2 = add2(rsum2, p2);
+                  pk[i] = pack_bf16x2_from(p2);
+                } else {                                                      // MUFU.EX2
+                  float x0, x1;
+                  unpack2(t2, x0, x1);
+                  const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                  rsum2 = add2(rsum2, pack2(p0, p1));
+                  pk[i] = pack_bf16x2(p0, p1);
+                }
               }
               const uint32_t slot = static_cast<uint32_t>(((c & 1) * 4 + k) ^ (row_local & 7));
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
@@ -381,22 +413,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const f32x2 il2 = splat2(1.0f / l_run);
       // normalised row -> this warp's 32-row slab of the (now idle) P buffer -> TMA store in 'b n (h d)' order;
       // rows past nq are clipped by the tensor map
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t ov[32];
-        tmem_ld_32x32b_x32(tPV + c * 32, ov);
+      {
+        uint32_t oa[32], ob[32];                                                // both halves in flight, one wait
+        tmem_ld_32x32b_x32(tPV, oa);
+        tmem_ld_32x32b_x32(tPV + 32, ob);
         tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          uint32_t pk[4];
+        for (int c = 0; c < 2; ++c) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int d = k * 4 + i;                                          // pair index within this half
-            pk[i] = pack_bf16x2_from(mul2(pack2u(ov[2 * d], ov[2 * d + 1]), il2));
+          for (int k = 0; k < 4; ++k) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int d = k * 4 + i;                                          // pair index within this half
+              pk[i] = pack_bf16x2_from(mul2(c == 0 ? pack2u(oa[2 * d], oa[2 * d + 1]) : pack2u(ob[2 * d], ob[2 * d + 1]), il2));
+            }
+            const uint32_t slot = static_cast<uint32_t>((c * 4 + k) ^ (row_local & 7));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                         "r"(pk[3]) : "memory");
           }
-          const uint32_t slot = static_cast<uint32_t>((c * 4 + k) ^ (row_local & 7));
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
-                       "r"(pk[3]) : "memory");
         }
       }
       tcgen05_fence_before();

@@ -74,10 +74,10 @@ struct GemmBf16 {
   //   out = rstd[m] * (acc - mu[m] * ln_c1[n]) + bias[n], with (mu, rstd) of row m reduced in the epilogue from the
   //   ln_parts (sum, sumsq) partials of that row (the stats_out format below) over 1 / ln_inv_d elements.
   const float* ln_c1 = nullptr;
-  const float* ln_stats = nullptr;      // [M, ln_parts, 2]
+  const float* ln_stats = nullptr;      // [ln_parts, M, 2]
   int ln_parts = 0;
   float ln_inv_d = 0.f;
-  // Emit (sum, sumsq) of every 64-column chunk of the stored bf16 output rows: [M, N/64, 2]
+  // Emit (sum, sumsq) of every 64-column chunk of the stored bf16 output rows: [N/64, M, 2]
   float* stats_out = nullptr;
   int stats_parts = 0;
 };

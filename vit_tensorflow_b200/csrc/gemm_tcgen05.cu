@@ -32,32 +32,37 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-#ifndef VB_GEMM_EW
-#define VB_GEMM_EW 2                     // epilogue warps per TMEM lane quarter for 256-wide tiles (2 or 3)
+#ifndef VB_GEMM_EW_NORES
+#define VB_GEMM_EW_NORES 3               // epilogue warps per TMEM lane quarter, 256-wide tiles WITHOUT a residual operand (2 or 3)
 #endif
-#ifndef VB_GEMM_STORE_WAIT1
-#define VB_GEMM_STORE_WAIT1 0
-#endif
-constexpr int MAX_EPI_WARPS = 4 * VB_GEMM_EW;   // epilogue warps (TMEM lane quarter = warp % 4, chunk lane = warp / 4)
-constexpr int PRODUCER_WARP = MAX_EPI_WARPS;    // the issue arbiter favours high warp ids: keep the two latency-critical
-constexpr int MMA_WARP = MAX_EPI_WARPS + 1;     // single-instruction-stream roles above the math-heavy epilogue warps
-constexpr int NUM_THREADS = (MAX_EPI_WARPS + 2) * 32;
 constexpr int STAGING_BYTES = 4096;       // per-warp slab: 32 rows x 64 bf16 columns (128-byte swizzled rows)
-constexpr int CONST_BYTES = 0;
+constexpr int CONST_BYTES = 2048;         // folded LayerNorm: (mean, rstd) of the tile's 128 rows, double-buffered
 
-template <int BN, int CG>
+// RES decides the epilogue organisation.  With a residual operand (to_out, fc2, patch embedding) a warp needs two 4 KB slabs
+// (residual-in of the next chunk / output of this one) and 2 warps per TMEM lane quarter keep the 5-stage operand ring.  Without
+// one (to_qkv, fc1 + GELU -- the LayerNorm-folded, epilogue-heavy GEMMs whose MMA warp measured 4-6 K cycles of tmem_empty
+// wait every other tile with 8 epilogue warps) one slab per warp is enough, so 12 warps (3 per sub-partition) fit beside the
+// same ring; their chunk body runs on 32-column halves to stay inside the 136 registers a 480-thread CTA allows.
+template <int BN, int CG, bool RES>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;               // each CTA of a pair stages half of B
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int CPT = BN / 64;                               // 64-column chunks per tile
-  static constexpr int EW = CPT >= 3 ? VB_GEMM_EW : 2;                       // epilogue warps per TMEM lane quarter (<= CPT)
-  static constexpr int EPI_WARPS = 4 * EW;
-  static constexpr int NUM_STAGING = 2 * EPI_WARPS;                 // two 4 KB slabs per epilogue warp (residual-in / output, ping-pong)
+  static constexpr int EW = (CPT >= 3 && !RES) ? VB_GEMM_EW_NORES : 2;  // epilogue warps per TMEM lane quarter (<= CPT)
+  static constexpr int EPI_WARPS = 4 * EW;                          // TMEM lane quarter = warp % 4, chunk lane = warp / 4
+  static constexpr int PRODUCER_WARP = EPI_WARPS;                   // the issue arbiter favours high warp ids: keep the latency-critical
+  static constexpr int MMA_WARP = EPI_WARPS + 1;                    // single-instruction-stream roles above the math-heavy epilogue warps
+  static constexpr int STATS_WARP = EPI_WARPS + 2;                  // folded LayerNorm: (sum, sumsq) partials -> (mean, rstd), a tile ahead
+  static constexpr int NUM_THREADS = (EPI_WARPS + 3) * 32;
+  static constexpr int SLABS = RES ? 2 : 1;                         // 4 KB slabs per epilogue warp
+  static constexpr bool HALVES = EW >= 3;                           // chunk body on 32-column halves (register diet)
+  static constexpr int NUM_STAGING = SLABS * EPI_WARPS;
   static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - CONST_BYTES - 512 - 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator (power of two: 256 or 512)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NUM_STAGING * STAGING_BYTES + CONST_BYTES + 512 /*barriers*/ + 1024 /*align*/;
+  static_assert(8 * (2 * STAGES + 9 + 2 * EPI_WARPS) + 8 <= 512, "barrier area overflow");
 };
 
 // Exact-erf GELU (vit.py:34), written as  gelu(x) = x/2 - |x| * (E(|x|) - 1/2),  E(a) = erfc(a/sqrt2) / 2  (for x > 0
@@ -85,13 +90,14 @@ __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
 
 // EPI: 0 = no per-column addend, 1 = + bias[n], 2 = folded LayerNorm (c1 = ln_c1, c2 = bias)
 template <int BN, bool GELU, bool RES, int CG, int EPI>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Cfg<BN, CG, RES>::NUM_THREADS), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K,
                  const float* __restrict__ bias, const float* __restrict__ scale,
                  const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* ln_stats, int ln_parts,
                  float ln_inv_d, float2* __restrict__ stats_out, int stats_parts, long long* __restrict__ dbg) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, RES>;
+  constexpr int PRODUCER_WARP = C::PRODUCER_WARP, MMA_WARP = C::MMA_WARP, STATS_WARP = C::STATS_WARP;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_stage0 = smem_base;
@@ -105,6 +111,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_ptr_smem = bar_base + 8u * (2 * C::STAGES + 4);
   auto res_bar = [&](int w, int p) { return bar_base + 8u * (2 * C::STAGES + 5 + w * 2 + p); };   // per epilogue warp x slab
+  auto lnfull_bar = [&](int b) { return bar_base + 8u * (2 * C::STAGES + 5 + 2 * C::EPI_WARPS + b); };
+  auto lnempty_bar = [&](int b) { return bar_base + 8u * (2 * C::STAGES + 7 + 2 * C::EPI_WARPS + b); };
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to aligned base
 
   const int warp = threadIdx.x >> 5;
@@ -138,6 +146,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(tempty_bar(s), CG * C::EPI_WARPS);         // the leader counts both CTAs' epilogue warps
     }
     for (int w = 0; w < C::EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(lnfull_bar(b), 1); mbar_init(lnempty_bar(b), C::EPI_WARPS); }
     fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -233,6 +242,38 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == STATS_WARP) {
+    // ===================================================================== LayerNorm statistics (EPI == 2 only)
+    // The rows' statistics arrive as `ln_parts` (sum, sumsq) partials, one per 64-column chunk of the row, in the layout
+    // [part][M] that the producing residual GEMM's epilogue (or row_stats_bf16) wrote; this warp reduces them in a fixed
+    // order to (mean, rstd) for the 128 rows of every tile of this CTA, one or two tiles ahead of the epilogue warps, into
+    // a double-buffered 1 KB table.  It replaces the former row_stats_finalize_kernel (24 launches per ViT-B/16 forward)
+    // without putting global loads on the epilogue's critical path.  ln_stats may be a buffer that a LATER kernel of the
+    // stream overwrites, never this one (a folded GEMM has no stats_out).
+    if (EPI == 2) {
+      uint32_t it = 0;
+      for (int t = tile0; t < num_tiles; t += tile_step, ++it) {
+        const int buf = it & 1;
+        mbar_wait(lnempty_bar(buf), ((it >> 1) & 1u) ^ 1u);
+        const int r0 = (t / tiles_n) * TM + cta_rank * BM;
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int i = 0; i < ln_parts; ++i) {
+          const float2* p = ln_stats + static_cast<size_t>(i) * M + r0 + lane;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (r0 + lane + 32 * j < M) { const float2 v = __ldg(p + 32 * j); s1[j] += v.x; s2[j] += v.y; }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mu = s1[j] * ln_inv_d;
+          const float2 mr = make_float2(mu, rsqrtf(fmaxf(s2[j] * ln_inv_d - mu * mu, 0.f) + 1e-3f));
+          *reinterpret_cast<float2*>(smem_gen + (smem_consts - smem_base) + (buf * 128 + lane + 32 * j) * 8) = mr;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(lnfull_bar(buf));
+      }
+    }
   } else if (warp < C::EPI_WARPS) {
     // ===================================================================== epilogue (4 x EW warps)
     // Warp (q, j) owns accumulator rows [32q, 32q+32) (its TMEM lane quarter) and every EW-th 64-column chunk (one
@@ -244,29 +285,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int q = e & 3;
     const int j = e >> 2;
     const int row_local = q * 32 + lane;
-    const uint32_t slab0 = smem_staging + e * 2 * 4096;            // two slabs of 32 rows x 128 bytes, 1024-aligned
+    const uint32_t slab0 = smem_staging + e * C::SLABS * 4096;     // slab(s) of 32 rows x 128 bytes, 1024-aligned
     const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
     const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * CPT;
     uint32_t cnt = 0;                                              // chunks processed by this warp (slab = cnt & 1)
     uint32_t rph = 0;                                              // bit p = mbarrier phase of slab p's residual barrier
     // folded LayerNorm of the A operand: y = rstd * acc + (-rstd * mu) * c1[n] + c2[n]   (c2 arrives through `bias`);
-    // (mu, rstd) of this thread's row, prefetched one tile ahead
-    // The statistics arrive as the `ln_parts` (sum, sumsq) partials per row that the producing residual GEMM's epilogue (or
-    // row_stats_bf16) emitted, one per 64-column chunk; they are reduced here in a fixed order (the former
-    // row_stats_finalize_kernel, 24 launches per ViT-B/16 forward, folded into its only consumer).  ln_stats may be the
-    // buffer a LATER kernel of the stream overwrites, never this one (stats_out of a folded GEMM is a different row set).
-    auto ln_load = [&](int r) -> float2 {
-      const float2* p = ln_stats + static_cast<size_t>(r) * ln_parts;
-      float s1 = 0.f, s2 = 0.f;
-      for (int i = 0; i < ln_parts; ++i) { const float2 v = __ldg(p + i); s1 += v.x; s2 += v.y; }
-      const float mu = s1 * ln_inv_d;
-      return make_float2(mu, rsqrtf(fmaxf(s2 * ln_inv_d - mu * mu, 0.f) + 1e-3f));
-    };
-    float2 ln_next = make_float2(0.f, 1.f);
-    if (EPI == 2 && tile0 < num_tiles) {
-      const int r0 = (tile0 / tiles_n) * TM + cta_rank * BM + row_local;
-      if (r0 < M) ln_next = ln_load(r0);
-    }
+    // (mu, rstd) of this thread's row come from the statistics warp's table
     // Residual tiles come in through TMA (32 rows x 64 columns into the slab that will also stage the output), one
     // chunk ahead of the math.  Per-thread row reads (32 distinct 128-byte lines per LDG) saturated the LSU: clock64
     // traces showed ~4 K cycles per chunk in those loads, 2.4x the tile's MMA time at K = 768.
@@ -295,11 +320,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         m0 = (t / tiles_n) * TM + cta_rank * BM;
         n0 = (t % tiles_n) * BN;
         row = m0 + row_local;
-        ln_rstd2 = splat2(ln_next.y);
-        ln_nmr2 = splat2(-ln_next.x * ln_next.y);
-        if (EPI == 2 && t + tile_step < num_tiles) {
-          const int rn = ((t + tile_step) / tiles_n) * TM + cta_rank * BM + row_local;
-          if (rn < M) ln_next = ln_load(rn);
+        if (EPI == 2) {
+          const int buf = it & 1;
+          mbar_wait(lnfull_bar(buf), static_cast<uint32_t>(it >> 1) & 1u);
+          const float2 mr = *reinterpret_cast<const float2*>(smem_gen + (smem_consts - smem_base) + (buf * 128 + row_local) * 8);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(lnempty_bar(buf));
+          ln_rstd2 = splat2(mr.y);
+          ln_nmr2 = splat2(-mr.x * mr.y);
         }
         if (lane == 0 && q == 0) trace(1 + j, 10);
         mbar_wait(tfull_bar(acc), static_cast<uint32_t>(it >> 1) & 1u);
@@ -311,34 +339,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ncol0 = n0 + cc * 64;
         const bool col_ok = ncol0 < N;                              // N % 64 == 0: a chunk is entirely in or out
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cc * 64;
-        const uint32_t slab = slab0 + (cnt & 1u) * 4096;
+        const uint32_t slab = slab0 + (RES ? (cnt & 1u) * 4096 : 0u);
         const uint32_t srow = slab + lane * 128;
-        uint32_t v[4][16];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) tmem_ld_32x32b_x16(tcol + g * 16, v[g]);
-        // the OTHER slab was last read by the TMA store of the previous chunk: once that has drained, prefetch the next
-        // chunk's residual into it (or simply make it writable again)
-        if (lane == 0) {
-          // VB_GEMM_STORE_WAIT1 (experiment, off): without a residual prefetch only the slab of TWO chunks ago is about to
-          // be overwritten, so the store issued a moment ago may stay in flight
-          if (!RES && VB_GEMM_STORE_WAIT1) bulk_wait_group_read<1>(); else bulk_wait_group_read<0>();
-          if (RES) res_issue(cnt + 1);
-        }
-        tmem_ld_wait();
-        if (lane == 0 && q == 0) trace(1 + j, 30 + c);
-        if (RES && col_ok) {                                        // this chunk's residual has landed
-          mbar_wait(res_bar(e, cnt & 1u), (rph >> (cnt & 1u)) & 1u);
-          rph ^= 1u << (cnt & 1u);
-        }
-        __syncwarp();
-        if (lane == 0 && q == 0) trace(1 + j, 40 + c);
+        const bool last_of_tile = (kk + EW >= total_chunks) || (static_cast<int>((kk + EW) / CPT) != it);
+        // All of this warp's TMEM reads of the accumulator buffer are complete once the last chunk's values sit in registers:
+        // hand the buffer back to the MMA warp THEN, not after the chunk's math and store (a chunk body of ~3 K cycles that the
+        // round-1 kernel kept on the tensor core's critical path whenever the epilogue paced the tile).
+        auto release_acc = [&]() {
+          if (last_of_tile) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);   // the leader's MMA warp owns this barrier
+              else mbar_arrive(tempty_bar(acc));
+            }
+          }
+        };
         f32x2 st1 = 0ull, st2 = 0ull;                               // (sum, sum of squares) of the stored bf16 outputs
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        // 16 accumulator columns [ncol0 + 16 g, +16) of this thread's row: epilogue math, bf16, into the slab
+        auto process = [&](int g, const uint32_t (&vv)[16]) {
           const int ncol = ncol0 + g * 16;
           f32x2 f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = pack2u(v[g][2 * j], v[g][2 * j + 1]);
+          for (int j = 0; j < 8; ++j) f[j] = pack2u(vv[2 * j], vv[2 * j + 1]);
           if (col_ok) {
             if (EPI == 2) {
               const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(ln_c1 + ncol);
@@ -401,12 +424,52 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + slot * 16), "r"(pk[4 * k]), "r"(pk[4 * k + 1]),
                          "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3]) : "memory");
           }
+        };
+        if (!C::HALVES) {
+          uint32_t v[4][16];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) tmem_ld_32x32b_x16(tcol + g * 16, v[g]);
+          // the OTHER slab was last read by the TMA store of the previous chunk: once that has drained, prefetch the next
+          // chunk's residual into it (or, without a residual, make the single slab writable again)
+          if (lane == 0) {
+            bulk_wait_group_read<0>();
+            if (RES) res_issue(cnt + 1);
+          }
+          tmem_ld_wait();
+          release_acc();
+          if (lane == 0 && q == 0) trace(1 + j, 30 + c);
+          if (RES && col_ok) {                                        // this chunk's residual has landed
+            mbar_wait(res_bar(e, cnt & 1u), (rph >> (cnt & 1u)) & 1u);
+            rph ^= 1u << (cnt & 1u);
+          }
+          __syncwarp();
+          if (lane == 0 && q == 0) trace(1 + j, 40 + c);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) process(g, v[g]);
+        } else {
+          // 32-column halves: half the live accumulator registers (12 epilogue warps share the register file)
+          uint32_t v[2][16];
+          tmem_ld_32x32b_x16(tcol, v[0]);
+          tmem_ld_32x32b_x16(tcol + 16, v[1]);
+          if (lane == 0) bulk_wait_group_read<0>();                   // the single slab: the previous chunk's store has read it
+          tmem_ld_wait();
+          __syncwarp();
+          if (lane == 0 && q == 0) trace(1 + j, 30 + c);
+          process(0, v[0]);
+          process(1, v[1]);
+          tmem_ld_32x32b_x16(tcol + 32, v[0]);
+          tmem_ld_32x32b_x16(tcol + 48, v[1]);
+          tmem_ld_wait();
+          release_acc();
+          if (lane == 0 && q == 0) trace(1 + j, 40 + c);
+          process(2, v[0]);
+          process(3, v[1]);
         }
         if (stats_out != nullptr && col_ok && row < M) {
           float a0, a1, b0, b1;
           unpack2(st1, a0, a1);
           unpack2(st2, b0, b1);
-          stats_out[static_cast<size_t>(row) * stats_parts + (ncol0 >> 6)] = make_float2(a0 + a1, b0 + b1);
+          stats_out[static_cast<size_t>(ncol0 >> 6) * M + row] = make_float2(a0 + a1, b0 + b1);   // [part][M]: coalesced over the rows
         }
         if (lane == 0 && q == 0) trace(1 + j, 50 + c);
         fence_proxy_async_smem();
@@ -416,15 +479,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           bulk_commit_group();
         }
         if (lane == 0 && q == 0) trace(1 + j, 20 + c);
-      }
-      if (kk + EW >= total_chunks || static_cast<int>((kk + EW) / CPT) != it) {
-        // my last chunk of this tile: all my TMEM reads of this accumulator buffer are complete (tcgen05.wait::ld above)
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (CG == 2) mbar_arrive_cluster(tempty_bar(acc) & kPeerBitMask);   // the leader's MMA warp owns this barrier
-          else mbar_arrive(tempty_bar(acc));
-        }
       }
     }
     if (lane == 0) bulk_wait_group_read<0>();   // the slab must outlive the store's reads; the writes drain before the grid completes
@@ -466,11 +520,11 @@ template <int BN, bool GELU, bool RES, int CG, int EPI>
 void launch(const GemmBf16& g, cudaStream_t stream) {
   auto kern = gemm_bf16_kernel<BN, GELU, RES, CG, EPI>;
   static unsigned long long seen[4] = {0, 0, 0, 0};
-  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG>::SMEM_BYTES));
+  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG, RES>::SMEM_BYTES));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.grid);
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg<BN, CG>::SMEM_BYTES;
+  cfg.blockDim = dim3(Cfg<BN, CG, RES>::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<BN, CG, RES>::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;

@@ -575,19 +575,7 @@ __global__ void row_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, f
       s2 = fmaf(a, a, fmaf(b, b, s2));
     }
   }
-  stats[idx] = make_float2(s1, s2);
-}
-
-__global__ void row_stats_finalize_kernel(const float2* __restrict__ stats, float2* __restrict__ rows, int M, int parts, float inv_d) {
-  asm volatile("griddepcontrol.wait;" ::: "memory");                 // PDL: the producer GEMM's statistics are complete
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");    // single wave: let the consumer GEMM start its prologue
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
-  const float2* p = stats + static_cast<long long>(m) * parts;
-  float s1 = 0.f, s2 = 0.f;
-  for (int i = 0; i < parts; ++i) { const float2 v = p[i]; s1 += v.x; s2 += v.y; }
-  const float mu = s1 * inv_d;
-  rows[m] = make_float2(mu, rsqrtf(fmaxf(s2 * inv_d - mu * mu, 0.f) + 1e-3f));
+  stats[static_cast<long long>(c) * M + m] = make_float2(s1, s2);      // [part][M], the layout the GEMM epilogue emits
 }
 
 __global__ void pad_heads_kernel(const float* __restrict__ W, float* __restrict__ Wp, int other, int groups, int heads, int dh, int dhp,
@@ -775,21 +763,6 @@ void ln_fold_consts(const float* W, const __nv_bfloat16* Wt, int ldw, const floa
                     int K, int N, cudaStream_t s) {
   ln_fold_consts_kernel<<<(N + 7) / 8, 256, 0, s>>>(W, Wt, ldw, beta, bias, c1, c2, K, N);
   VB_LAUNCHED();
-}
-
-void row_stats_finalize(const float* stats, float* rows, int M, int parts, int D, cudaStream_t s) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((M + 255) / 256);
-  cfg.blockDim = dim3(256);
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  VB_CUDA(cudaLaunchKernelEx(&cfg, row_stats_finalize_kernel, reinterpret_cast<const float2*>(stats), reinterpret_cast<float2*>(rows), M,
-                             parts, 1.0f / static_cast<float>(D)));
-  count_launch();
 }
 
 void row_stats_bf16(const __nv_bfloat16* X, int ldx, float* stats, int M, int D, cudaStream_t s) {

@@ -81,10 +81,9 @@ void pad_heads_f32(const float* W, float* Wp, int other, int groups, int heads, 
 //   c2[n] = sum_k beta[k] * W[k,n] + (bias ? bias[n] : 0)
 void ln_fold_consts(const float* W, const __nv_bfloat16* Wt, int ldw, const float* beta, const float* bias, float* c1, float* c2,
                     int K, int N, cudaStream_t s);
-// stats[m, c] = (sum, sum of squares) of X[m, 64c .. 64c+63]  (same format the GEMM epilogue emits); D % 64 == 0
+// stats[c, m] = (sum, sum of squares) of X[m, 64c .. 64c+63]  ([D/64][M] float2: the format the GEMM epilogue emits and the
+// LayerNorm-folded GEMM's statistics warp reduces); D % 64 == 0
 void row_stats_bf16(const __nv_bfloat16* X, int ldx, float* stats, int M, int D, cudaStream_t s);
-// rows[m] = (mean, rsqrt(var + 1e-3)) from the `parts` (sum, sumsq) partials of row m over D elements (fixed order)
-void row_stats_finalize(const float* stats, float* rows, int M, int parts, int D, cudaStream_t s);
 
 long long launch_counter();      // number of kernel launches issued through these wrappers (process-wide)
 void count_launch(int n = 1);
