@@ -40,6 +40,12 @@ CONFIGS = {
     "cait_s36": dict(kind="cait", image_size=224, patch_size=16, num_classes=1000, dim=384, depth=36, cls_depth=2, heads=8,
                      mlp_dim=1536, dim_head=48, batch=128),
     "vit_l16_384": dict(kind="vit", image_size=384, patch_size=16, num_classes=1000, dim=1024, depth=24, heads=16, mlp_dim=4096, batch=128),
+    # the reference README's usage examples of the two remaining hot-path model classes (README.md:327-345, :208-216)
+    "crossvit_readme": dict(kind="crossvit", image_size=256, num_classes=1000, depth=4, sm_dim=192, sm_patch_size=16, sm_enc_depth=2,
+                            sm_enc_heads=8, sm_enc_mlp_dim=2048, lg_dim=384, lg_patch_size=64, lg_enc_depth=3, lg_enc_heads=8,
+                            lg_enc_mlp_dim=2048, cross_attn_depth=2, cross_attn_heads=8, batch=256),
+    "t2t_readme": dict(kind="t2t_vit", image_size=224, num_classes=1000, dim=512, depth=5, heads=8, mlp_dim=512,
+                       t2t_layers=((7, 4), (3, 2), (3, 2)), batch=64),
 }
 METRIC = "images/sec ViT-B/16 224^2 bf16 forward"
 

@@ -144,6 +144,28 @@ def test_attention(lib, precision, variant, B, nq, nk, heads, dh):
         _assert_close_sigma(out, ref, ATTN_BF16_SIGMA[variant], ATTN_BF16_REL)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("B,nq,nk,heads,dh", [(2, 130, 130, 8, 64), (1, 64, 256, 16, 32), (3, 65, 65, 8, 16), (2, 5, 37, 16, 48),
+                                               (1, 256, 256, 8, 48), (5, 197, 197, 16, 64), (2, 16, 16, 8, 64), (150, 70, 70, 8, 32)])
+def test_attention_mix_shapes(lib, variant, B, nq, nk, heads, dh):
+    """Fused tcgen05 head-mixing attention (attn_mix_tcgen05.cu; deepvit.py:79-87, cait.py:121-127) at the edges of its tiling:
+    partial 64-row query tiles (nq = 130, 65, 5), a single key block, the 256-key limit, key counts that leave the second
+    block of a super-block empty (nk = 16, 37, 70), dim_head 16 / 32 / 48 / 64, more items than CTAs (B = 150 x 2 tiles)."""
+    from vit_tensorflow_b200 import _lib
+    rng = np.random.default_rng(nq * 31 + nk + variant)
+    inner = heads * dh
+    q = bf16_round(rng.standard_normal((B, nq, inner), dtype=np.float32))
+    k = bf16_round(rng.standard_normal((B, nk, inner), dtype=np.float32))
+    v = bf16_round(rng.standard_normal((B, nk, inner), dtype=np.float32))
+    mix_a = rng.standard_normal((heads, heads)).astype(np.float32)
+    mix_b = rng.standard_normal((heads, heads)).astype(np.float32) if variant == 2 else None
+    g = rng.uniform(0.5, 1.5, heads).astype(np.float32) if variant == 1 else None
+    b = rng.standard_normal(heads).astype(np.float32) if variant == 1 else None
+    out, _ = _lib.op_attention(q, k, v, heads, variant, mix_a, mix_b, g, b, "bf16")
+    ref = _attention_ref(q, k, v, heads, variant, mix_a, mix_b, g, b)
+    _assert_close_sigma(out, ref, ATTN_BF16_SIGMA[variant], ATTN_BF16_REL)
+
+
 # bf16 attention bound: |err| <= SIGMA * std(ref) + REL * |ref|  (measured maxima: DESIGN.md section 6)
 ATTN_BF16_SIGMA = {0: 1.5e-2, 1: 1.5e-2, 2: 1.5e-2}
 ATTN_BF16_REL = 1.0e-2

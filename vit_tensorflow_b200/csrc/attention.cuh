@@ -29,6 +29,21 @@ bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16*
                            __nv_bfloat16* out, int ldo, float* S, int B, int nq, int nk, int heads, int dh, int variant,
                            const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta, cudaStream_t s);
 
+// Head-mix weights as kernel parameters (heads <= 16): wa = pre-softmax mix (CaiT) / re-attention weights (DeepViT), wb = CaiT's
+// post-softmax mix, both [h][g] with row pitch `heads`; gamma / beta = DeepViT's LayerNorm over heads.
+struct MixParams {
+  float wa[256];
+  float wb[256];
+  float gamma[16], beta[16];
+};
+bool attention_mix_params(const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta, int heads,
+                          cudaStream_t s, MixParams* out);
+
+// Fused tcgen05 head-mixing attention (attn_mix_tcgen05.cu): variants 1 / 2, heads 8 / 16, dim_head <= 64, nk <= 256.
+bool attention_mix(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,
+                   __nv_bfloat16* out, int ldo, int B, int nq, int nk, int heads, int dh, int variant, const float* mix_a,
+                   const float* mix_b, const float* ln_gamma, const float* ln_beta, cudaStream_t s, float scale = 0.f);
+
 // One-kernel attention for a single query row per image (CaiT class attention, CrossViT cross attention; any variant):
 // attn_cls.cu.  false if the shape is not covered.
 bool attention_cls(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,

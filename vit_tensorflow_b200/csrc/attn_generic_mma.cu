@@ -294,11 +294,6 @@ scores_stripe_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bf
 // shuffles, and there is no shared memory and no block barrier.  Rows are read as fp32 scores and rewritten IN PLACE
 // (row pitch `lds` floats >= 16-aligned nk) as bf16 probabilities: hi plane in the first nkp bf16 of the row, and for
 // DeepViT the lo plane (p - hi) in the next nkp, so the PV product can feed them to mma.sync without conversion.
-struct MixParams {
-  float wa[256];        // [H][H] pre-softmax mix (v2) / re-attention (v1)
-  float wb[256];        // [H][H] post-softmax mix (v2)
-  float gamma[16], beta[16];
-};
 
 template <int H>
 __device__ __forceinline__ float tree_sum(const float (&v)[H]) {           // pairwise: depth log2(H) instead of H
@@ -549,27 +544,8 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
   if (reinterpret_cast<uintptr_t>(v) % 16 != 0 || reinterpret_cast<uintptr_t>(S) % 16 != 0) return false;
   const int nkp = (nk + 15) & ~15;
   const int lds = nkp;
-  const MixKey key{mix_a, mix_b, ln_gamma, ln_beta};
-  MixParams mixp;                                                // copied out under the lock (handles on other threads may clear the cache)
-  bool cached = false;
-  {
-    std::lock_guard<std::mutex> lock(global_cache_mutex());       // weights are immutable between attention_mix_cache_clear() calls
-    auto& cache = mix_cache();
-    auto it = cache.find(key);
-    if (it != cache.end()) { mixp = it->second; cached = true; }
-  }
-  if (!cached) {
-    MixParams P = {};
-    const size_t hh = static_cast<size_t>(heads) * heads * sizeof(float);
-    VB_CUDA(cudaStreamSynchronize(s));
-    if (mix_a) VB_CUDA(cudaMemcpy(P.wa, mix_a, hh, cudaMemcpyDeviceToHost));
-    if (mix_b) VB_CUDA(cudaMemcpy(P.wb, mix_b, hh, cudaMemcpyDeviceToHost));
-    if (ln_gamma) VB_CUDA(cudaMemcpy(P.gamma, ln_gamma, heads * sizeof(float), cudaMemcpyDeviceToHost));
-    if (ln_beta) VB_CUDA(cudaMemcpy(P.beta, ln_beta, heads * sizeof(float), cudaMemcpyDeviceToHost));
-    mixp = P;
-    std::lock_guard<std::mutex> lock(global_cache_mutex());
-    mix_cache()[key] = P;
-  }
+  MixParams mixp;
+  if (!attention_mix_params(mix_a, mix_b, ln_gamma, ln_beta, heads, s, &mixp)) return false;
   const float scale = 1.0f / sqrtf(static_cast<float>(dh));
   {
     const int sc_smem = (64 + ((nk + 7) & ~7)) * (dh + 8) * 2 + 32;   // +32: the last ldmatrix.x4 of a dh = 48 row touches its pad
@@ -617,6 +593,32 @@ bool attention_rows_path(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k
 void attention_mix_cache_clear() {
   std::lock_guard<std::mutex> lock(global_cache_mutex());
   mix_cache().clear();
+}
+
+// The head-mix weights are tiny and constant per layer: they are read back from the device once per pointer set and then travel
+// as kernel parameters (constant-bank operands).  The value is copied out under the lock: handles on other threads may clear the
+// cache.  The first use of a pointer set synchronises the stream (never inside a stream capture: first calls are eager).
+bool attention_mix_params(const float* mix_a, const float* mix_b, const float* ln_gamma, const float* ln_beta, int heads,
+                          cudaStream_t s, MixParams* out) {
+  if (heads > 16 || heads < 1) return false;
+  const MixKey key{mix_a, mix_b, ln_gamma, ln_beta};
+  {
+    std::lock_guard<std::mutex> lock(global_cache_mutex());       // weights are immutable between attention_mix_cache_clear() calls
+    auto& cache = mix_cache();
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
+  }
+  MixParams P = {};
+  const size_t hh = static_cast<size_t>(heads) * heads * sizeof(float);
+  VB_CUDA(cudaStreamSynchronize(s));
+  if (mix_a) VB_CUDA(cudaMemcpy(P.wa, mix_a, hh, cudaMemcpyDeviceToHost));
+  if (mix_b) VB_CUDA(cudaMemcpy(P.wb, mix_b, hh, cudaMemcpyDeviceToHost));
+  if (ln_gamma) VB_CUDA(cudaMemcpy(P.gamma, ln_gamma, heads * sizeof(float), cudaMemcpyDeviceToHost));
+  if (ln_beta) VB_CUDA(cudaMemcpy(P.beta, ln_beta, heads * sizeof(float), cudaMemcpyDeviceToHost));
+  *out = P;
+  std::lock_guard<std::mutex> lock(global_cache_mutex());
+  mix_cache()[key] = P;
+  return true;
 }
 
 bool attention_generic_mma(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int ldk, const __nv_bfloat16* v, int ldv,

@@ -57,9 +57,12 @@ constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_
 // bits 23-31, which wraps correctly for negative n).  t <= 8 by the lazy-rescale invariant; t is clamped at -126 (result ~1e-38).
 // Per PAIR of elements: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 SHL + 2 IADD, against 2 MUFU.EX2 (16 issue cycles of the 4-lane
 // MUFU unit per 64 elements): the two paths run on different pipes, so splitting the 8-key groups between them shortens the
-// exp phase that paced the item (profiles/r01_attn_item_timeline.md: 4.8 K of 10.4 K cycles at 1.3x the MUFU floor).
+// exp phase (profiles/r01_attn_item_timeline.md: 4.8 K of 10.4 K cycles at 1.3x the MUFU floor).  MEASURED (round 2,
+// profiles/r02_ab_attn_poly.txt, ViT-B/16 B = 256 shapes, one box): mask 0x0 117.2 us, 0x8 (25 %) 116.4 us, 0xA (50 %) 121.2 us,
+// 0xE (75 %) 131.6 us -- the kernel is not MUFU-bound (nor issue-bound: ~1400 warp instructions per sub-partition and item in
+// 10.4 K cycles); the serial S -> softmax -> P -> PV round trips of the two warps per sub-partition are.  Default: off.
 #ifndef VB_ATTN_POLY_MASK
-#define VB_ATTN_POLY_MASK 0xA            // bit k: the k-th 8-key group of every 32-key chunk takes the polynomial path
+#define VB_ATTN_POLY_MASK 0x0            // bit k: the k-th 8-key group of every 32-key chunk takes the polynomial path
 #endif
 __device__ __forceinline__ f32x2 ex2_poly2(f32x2 t) {
   float t0, t1;
@@ -476,7 +479,8 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
                                    const float* mix_a, const float* mix_b, const float* ln_g, const float* ln_b, cudaStream_t s,
                                    float scale) {
   if (nq == 1 && attention_cls(q, ldq, k, ldk, v, ldv, out, ldo, B, nk, heads, dh, variant, mix_a, mix_b, ln_g, ln_b, s, scale)) return true;
-  if (variant != 0 || dh != DH || nq < 2) return false;    // head-mixing variants: attn_mix path / generic path
+  if (variant != 0) return attention_mix(q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads, dh, variant, mix_a, mix_b, ln_g, ln_b, s, scale);
+  if (dh != DH || nq < 2) return false;
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return false;
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
        reinterpret_cast<uintptr_t>(out)) % 16) return false;

@@ -62,6 +62,8 @@ CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2
 struct GemmBf16 {
   CUtensorMap tmap_a, tmap_b, tmap_c, tmap_r;   // A, B (weights), output, residual
   int M = 0, N = 0, K = 0;
+  __nv_bfloat16* out = nullptr;         // [M, ldc] (the epilogue stores rows straight from registers)
+  int ldc = 0;
   int block_n = 256;
   int cta_group = 2;                    // 2: CTA pairs (cta_group::2) on 256-row tiles; 1: single-CTA 128-row tiles
   const float* bias = nullptr;          // [N] or null

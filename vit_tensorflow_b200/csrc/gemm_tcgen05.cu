@@ -32,6 +32,9 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
+#ifndef VB_GEMM_DIRECT_STORE
+#define VB_GEMM_DIRECT_STORE 1            // 1: epilogue rows go registers -> global (STG.256); 0: registers -> smem slab -> TMA store
+#endif
 #ifndef VB_GEMM_EW_NORES
 #define VB_GEMM_EW_NORES 3               // epilogue warps per TMEM lane quarter, 256-wide tiles WITHOUT a residual operand (2 or 3)
 #endif
@@ -55,7 +58,9 @@ struct Cfg {
   static constexpr int MMA_WARP = EPI_WARPS + 1;                    // single-instruction-stream roles above the math-heavy epilogue warps
   static constexpr int STATS_WARP = EPI_WARPS + 2;                  // folded LayerNorm: (sum, sumsq) partials -> (mean, rstd), a tile ahead
   static constexpr int NUM_THREADS = (EPI_WARPS + 3) * 32;
-  static constexpr int SLABS = RES ? 2 : 1;                         // 4 KB slabs per epilogue warp
+  // 4 KB slabs per epilogue warp: residual-in (double-buffered, prefetched one chunk ahead) and, with the TMA-store
+  // epilogue, the output staging (shared with the residual slab)
+  static constexpr int SLABS = RES ? 2 : (VB_GEMM_DIRECT_STORE ? 0 : 1);
   static constexpr bool HALVES = EW >= 3;                           // chunk body on 32-column halves (register diet)
   static constexpr int NUM_STAGING = SLABS * EPI_WARPS;
   static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - CONST_BYTES - 512 - 1024) / STAGE_BYTES;
@@ -93,7 +98,7 @@ template <int BN, bool GELU, bool RES, int CG, int EPI>
 __global__ void __launch_bounds__((Cfg<BN, CG, RES>::NUM_THREADS), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K,
-                 const float* __restrict__ bias, const float* __restrict__ scale,
+                 __nv_bfloat16* __restrict__ out, int ldc, const float* __restrict__ bias, const float* __restrict__ scale,
                  const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* ln_stats, int ln_parts,
                  float ln_inv_d, float2* __restrict__ stats_out, int stats_parts, long long* __restrict__ dbg) {
   using C = Cfg<BN, CG, RES>;
@@ -286,6 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int j = e >> 2;
     const int row_local = q * 32 + lane;
     const uint32_t slab0 = smem_staging + e * C::SLABS * 4096;     // slab(s) of 32 rows x 128 bytes, 1024-aligned
+    const bool st256 = (ldc % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 32 == 0);   // 32-byte aligned 16-column groups
     const int my_tiles = tile0 < num_tiles ? (num_tiles - tile0 + tile_step - 1) / tile_step : 0;
     const uint32_t total_chunks = static_cast<uint32_t>(my_tiles) * CPT;
     uint32_t cnt = 0;                                              // chunks processed by this warp (slab = cnt & 1)
@@ -418,11 +424,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               st2 = fma2(ab, ab, st2);
             }
           }
+          if (VB_GEMM_DIRECT_STORE) {
+            // Registers -> global: this thread's 16 columns are 32 contiguous bytes of its output row = one full sector per lane
+            // and store (STG.256).  The smem round trip of the TMA-store epilogue (64 KB written + 64 KB read per 128 x 256 tile)
+            // competed with the mainloop for the 128 B/clk shared-memory port that TMA writes + UMMA reads already saturate at
+            // full MMA rate: the K = 768 GEMMs ran at 1427 / (1 + epilogue bytes / mainloop bytes) TF/s (1205 without, 1098 with a
+            // residual operand against 1427 at K = 3072, profiles/r02_ab_gemm_epilogue.txt).
+            if (col_ok && row < M) {
+              __nv_bfloat16* orow = out + static_cast<size_t>(row) * ldc + ncol;
+              if (st256) {
+                asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(orow), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                             "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+              } else {
+                asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(orow), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(orow + 8), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+              }
+            }
+          } else {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const uint32_t slot = static_cast<uint32_t>((g * 2 + k) ^ (lane & 7));   // 128B swizzle: 16-byte slot ^ (row % 8)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + slot * 16), "r"(pk[4 * k]), "r"(pk[4 * k + 1]),
-                         "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3]) : "memory");
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t slot = static_cast<uint32_t>((g * 2 + k) ^ (lane & 7));   // 128B swizzle: 16-byte slot ^ (row % 8)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + slot * 16), "r"(pk[4 * k]), "r"(pk[4 * k + 1]),
+                           "r"(pk[4 * k + 2]), "r"(pk[4 * k + 3]) : "memory");
+            }
           }
         };
         if (!C::HALVES) {
@@ -432,7 +456,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // the OTHER slab was last read by the TMA store of the previous chunk: once that has drained, prefetch the next
           // chunk's residual into it (or, without a residual, make the single slab writable again)
           if (lane == 0) {
-            bulk_wait_group_read<0>();
+            if (!VB_GEMM_DIRECT_STORE) bulk_wait_group_read<0>();
+            else if (RES) fence_proxy_async_smem();                     // this warp's ld.shared of that slab precede the TMA write
             if (RES) res_issue(cnt + 1);
           }
           tmem_ld_wait();
@@ -451,7 +476,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint32_t v[2][16];
           tmem_ld_32x32b_x16(tcol, v[0]);
           tmem_ld_32x32b_x16(tcol + 16, v[1]);
-          if (lane == 0) bulk_wait_group_read<0>();                   // the single slab: the previous chunk's store has read it
+          if (!VB_GEMM_DIRECT_STORE && lane == 0) bulk_wait_group_read<0>();   // the single slab: the previous chunk's store has read it
           tmem_ld_wait();
           __syncwarp();
           if (lane == 0 && q == 0) trace(1 + j, 30 + c);
@@ -472,16 +497,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           stats_out[static_cast<size_t>(ncol0 >> 6) * M + row] = make_float2(a0 + a1, b0 + b1);   // [part][M]: coalesced over the rows
         }
         if (lane == 0 && q == 0) trace(1 + j, 50 + c);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (col_ok) tma_store_2d(&tmap_c, slab, ncol0, m0 + q * 32);
-          bulk_commit_group();
+        if (!VB_GEMM_DIRECT_STORE) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (col_ok) tma_store_2d(&tmap_c, slab, ncol0, m0 + q * 32);
+            bulk_commit_group();
+          }
         }
         if (lane == 0 && q == 0) trace(1 + j, 20 + c);
       }
     }
-    if (lane == 0) bulk_wait_group_read<0>();   // the slab must outlive the store's reads; the writes drain before the grid completes
+    if (!VB_GEMM_DIRECT_STORE && lane == 0) bulk_wait_group_read<0>();   // the slab must outlive the store's reads; the writes drain before the grid completes
   }
 
   tcgen05_fence_before();
@@ -535,7 +562,7 @@ void launch(const GemmBf16& g, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.tmap_r, g.M, g.N, g.K, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
+  VB_CUDA(cudaLaunchKernelEx(&cfg, kern, g.tmap_a, g.tmap_b, g.tmap_c, g.tmap_r, g.M, g.N, g.K, g.out, g.ldc, g.bias, g.scale, g.res, g.ldr, g.ln_c1,
                              reinterpret_cast<const float2*>(g.ln_stats), g.ln_parts, g.ln_inv_d, reinterpret_cast<float2*>(g.stats_out),
                              g.stats_parts, gemm_trace_buffer()));
   count_launch();
@@ -609,6 +636,7 @@ GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt
   GemmBf16 g;
   g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.scale = scale; g.res = res; g.ldr = ldr; g.gelu = gelu;
+  g.out = out; g.ldc = ldc;
   // 256-wide tiles unless N only fills 128-wide ones well (e.g. CaiT dim 384) or the problem is tiny.
   g.block_n = (N % 256 == 0 || N >= 1024) ? 256 : 128;
   g.cta_group = (M > BM) ? 2 : 1;      // pair two SMs on 256-row tiles unless the whole problem is one 128-row tile

@@ -98,6 +98,12 @@ __device__ __forceinline__ void tcgen05_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 
+// Register reallocation between the warpgroups (4 consecutive warps) of a CTA: every warp of the warpgroup must execute it.
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 // ------------------------------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
