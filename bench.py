@@ -201,8 +201,9 @@ def run_ours(args, c):
     import torch.distributed as dist
     import oracle
     from vit_tensorflow_b200 import build, from_config
-    from vit_tensorflow_b200.runtime import DataParallel, HostPipeline, init_distributed
+    from vit_tensorflow_b200.runtime import DataParallel, HostPipeline, NativeDataParallel, bind_to_gpu_numa, init_distributed
 
+    numa_node = bind_to_gpu_numa(int(os.environ.get("LOCAL_RANK", "0")))   # before any pinned allocation (first touch)
     rank, world, local = init_distributed("nccl")
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
@@ -215,7 +216,10 @@ def run_ours(args, c):
     cfg = oracle_cfg(c)
     B, H, W = c["batch"], cfg["image_h"], cfg["image_w"]
     model = from_config(cfg, precision=args.precision, device=local, seed=0)     # random-init weights, same on all ranks
-    dp = DataParallel(model, B, (H, W), rank, world)
+    # N > 1: the C-ABI's own data-parallel entry (vb_dp_init / vb_forward_allgather: forward + in-place ncclAllGather of the
+    # logits on one stream); N = 1: the plain forward (no collective exists)
+    native_dp = world > 1 and not args.torch_dp
+    dp = NativeDataParallel(model, B, (H, W), rank, world) if native_dp else DataParallel(model, B, (H, W), rank, world)
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     img_host = torch.randn((B, H, W, 3), generator=gen, dtype=torch.float32).pin_memory()
     img_dev = img_host.to(dev)
@@ -338,6 +342,9 @@ def run_ours(args, c):
                     dtype="bf16" if args.precision == "bf16" else "f32", data="synthetic",
                     config=dict(workload=args.config, kind=c["kind"], per_gpu_batch=B, global_batch=world * B,
                                 image=[H, W], parallelism=f"dp{world}", flops_per_image=flops_img,
+                                collective=("vb_forward_allgather (C-ABI, NCCL all-gather of the logits)" if native_dp else
+                                            ("torch.distributed all_gather_into_tensor" if world > 1 else "none")),
+                                numa_node_rank0=numa_node,
                                 l2="inputs larger than L2 (154 MB images, >1 GB activations per step; no flush needed)",
                                 weights="random init (reference distributions), seed 0"),
                     e2e=e2e, gpu_launches=int(launches_per_step * args.steps), clocks=clocks_out, roofline=roof,
@@ -358,6 +365,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=None, help="override the per-GPU batch of the config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--torch-dp", action="store_true", help="N > 1: torch.distributed for the all-gather instead of the C-ABI's own NCCL path")
     args = ap.parse_args()
     c = dict(CONFIGS[args.config])
     if args.batch:

@@ -61,6 +61,9 @@ constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_
 // profiles/r02_ab_attn_poly.txt, ViT-B/16 B = 256 shapes, one box): mask 0x0 117.2 us, 0x8 (25 %) 116.4 us, 0xA (50 %) 121.2 us,
 // 0xE (75 %) 131.6 us -- the kernel is not MUFU-bound (nor issue-bound: ~1400 warp instructions per sub-partition and item in
 // 10.4 K cycles); the serial S -> softmax -> P -> PV round trips of the two warps per sub-partition are.  Default: off.
+#ifndef VB_ATTN_PINGPONG
+#define VB_ATTN_PINGPONG 1
+#endif
 #ifndef VB_ATTN_POLY_MASK
 #define VB_ATTN_POLY_MASK 0x0            // bit k: the k-th 8-key group of every 32-key chunk takes the polynomial path
 #endif
@@ -262,11 +265,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t tS = lane_addr + TM_S + t * 128, tPV = lane_addr + TM_PV + t * 64;
     const uint32_t sPt = sP + t * P_BYTES + row_local * 128;
     uint32_t sc = 0, pvc = 0;
+    if (VB_ATTN_PINGPONG && t == 1) named_bar_arrive(2, 256);              // tile 0 opens every item
     for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
       const int pair = it % pairs, bh = it / pairs;
       const int h = bh % heads, b = bh / heads;
       const int q0 = pair * 2 * BQ + t * BQ;
       if (q0 >= nq) continue;                                             // this item has a single tile
+      const bool pingpong = VB_ATTN_PINGPONG && (pair * 2 * BQ + BQ < nq);  // both tiles of the item exist
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int valid = min(BKV, nk - j * BKV);
@@ -277,10 +282,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         if (wq == 0 && lane == 0) trace(1 + t, 20 + j);
         // the only TMEM read of S: this row's 128 scores
         uint32_t v0[32], v1[32], v2[32], v3[32];
-        tmem_ld_32x32b_x32(tS, v0);
-        tmem_ld_32x32b_x32(tS + 32, v1);
-        tmem_ld_32x32b_x32(tS + 64, v2);
-        tmem_ld_32x32b_x32(tS + 96, v3);
+        tmem_ld_32x32b_x32(tS, v0);                                       // 32-key chunks past `valid` are never read: the TMEM ->
+        if (valid > 32) tmem_ld_32x32b_x32(tS + 32, v1);                  // register path (64 B/clk/SM) is as scarce as the MUFU
+        if (valid > 64) tmem_ld_32x32b_x32(tS + 64, v2);
+        if (valid > 96) tmem_ld_32x32b_x32(tS + 96, v3);
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -396,10 +401,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           if (lane == 0) bulk_wait_group_read<0>();
           __syncwarp();
         }
+        // Ping-pong of the two tiles' exponential phases (VB_ATTN_PINGPONG): a named-barrier token makes the groups take turns, so
+        // that one tile's MUFU / FP32 phase runs against the other's TMEM-load + row-max phase instead of both contending for the
+        // same unit in lock step (the shared K/V ring re-aligned the tiles at every block; a start-up offset alone measured nothing).
+        if (pingpong) named_bar_sync(2 + t, 256);
         emit(0, v0);
         emit(1, v1);
         emit(2, v2);
         emit(3, v3);
+        if (pingpong) named_bar_arrive(2 + (t ^ 1), 256);
         float rs0, rs1;
         unpack2(rsum2, rs0, rs1);
         l_run += rs0 + rs1;

@@ -33,7 +33,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;             // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 #ifndef VB_GEMM_DIRECT_STORE
-#define VB_GEMM_DIRECT_STORE 1            // 1: epilogue rows go registers -> global (STG.256); 0: registers -> smem slab -> TMA store
+#define VB_GEMM_DIRECT_STORE 0            // 0: registers -> smem slab -> TMA store; 1 (experiment): registers -> global (STG.256)
 #endif
 #ifndef VB_GEMM_EW_NORES
 #define VB_GEMM_EW_NORES 3               // epilogue warps per TMEM lane quarter, 256-wide tiles WITHOUT a residual operand (2 or 3)
@@ -425,11 +425,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           if (VB_GEMM_DIRECT_STORE) {
-            // Registers -> global: this thread's 16 columns are 32 contiguous bytes of its output row = one full sector per lane
-            // and store (STG.256).  The smem round trip of the TMA-store epilogue (64 KB written + 64 KB read per 128 x 256 tile)
-            // competed with the mainloop for the 128 B/clk shared-memory port that TMA writes + UMMA reads already saturate at
-            // full MMA rate: the K = 768 GEMMs ran at 1427 / (1 + epilogue bytes / mainloop bytes) TF/s (1205 without, 1098 with a
-            // residual operand against 1427 at K = 3072, profiles/r02_ab_gemm_epilogue.txt).
+            // EXPERIMENT (off): registers -> global, this thread's 16 columns = 32 contiguous bytes of its output row = one full
+            // sector per lane and store (STG.256), to take the epilogue's smem round trip (64 KB written + 64 KB read per
+            // 128 x 256 tile) off the shared-memory port the mainloop saturates.  MEASURED SLOWER (profiles/r02_ab_gemm_direct_store.txt,
+            // one box): to_qkv 1066 vs 1161 TF/s, fc1 + GELU 1051 vs 1129, dim-384 GEMMs 519 vs 599 -- 32 distinct lines per store
+            // instruction cost more in the LSU / L1 than the slab + one TMA store per chunk.
             if (col_ok && row < M) {
               __nv_bfloat16* orow = out + static_cast<size_t>(row) * ldc + ncol;
               if (st256) {

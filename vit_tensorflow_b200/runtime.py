@@ -41,6 +41,43 @@ def init_distributed(backend: str = "nccl"):
     return rank, world, local
 
 
+def gpu_numa_cpus(local_rank: int):
+    """CPUs of the NUMA node the GPU hangs off (sysfs: /sys/bus/pci/devices/<bus id>/numa_node -> node cpulist), or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return node, cpus
+    except Exception:
+        return None
+
+
+def bind_to_gpu_numa(local_rank: int):
+    """Pin this process (and therefore the pinned host buffers it allocates afterwards, first touch) to the CPUs of its GPU's
+    NUMA node: with eight ranks each streaming 154 MB of images per step, host reads that cross the socket interconnect are
+    what bends the end-to-end scaling curve (GPUs 4-7 sit on node 1).  Returns the node or None when the topology is not
+    visible / the allowed CPU set does not intersect it."""
+    info = gpu_numa_cpus(local_rank)
+    if info is None:
+        return None
+    node, cpus = info
+    try:
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def all_gather_logits(gathered, local, world: int):
     """In-place all-gather: `local` is this rank's slice of `gathered` ([world*B, classes])."""
     if world > 1:
@@ -90,7 +127,8 @@ class NativeDataParallel:
     handle to an NCCL communicator and `vb_forward_allgather` runs the forward and the in-place all-gather of the logits on one
     stream -- no torch.distributed on the data path.  The 128-byte communicator id travels by whatever the launcher has
     (here: an already initialised torch.distributed group of any backend, or `id_bytes` passed in by the caller).
-    NOT yet exercised on a multi-GPU box (no multi-GPU minutes were left in round 1); `DataParallel` is the measured path."""
+    This is the path `bench.py` measures for N > 1; tools/dp_check.py checks it bit for bit against `DataParallel` and
+    against the single-GPU forward of the whole batch."""
 
     def __init__(self, model, per_rank_batch: int, image_hw, rank: int = 0, world: int = 1, id_bytes: bytes | None = None):
         import ctypes as C
