@@ -37,6 +37,15 @@ for name in ops:
         b = rng.standard_normal(N).astype(np.float32)
         o, ms = _lib.op_ln_linear(a, g, bt, w, b, gelu, iters)      # times row_stats_bf16 + the folded GEMM
         out[name] = dict(ms=ms, tflops=2.0 * Mx * N * K / ms / 1e9, crc=zlib.crc32(o.tobytes()))
+    elif name in ("mix_cait", "mix_deepvit"):
+        B, n, h, dh, var = (128, 196, 8, 48, 2) if name == "mix_cait" else (128, 197, 16, 64, 1)
+        q, k, v = (rng.standard_normal((B, n, h * dh), dtype=np.float32) for _ in range(3))
+        a = rng.standard_normal((h, h)).astype(np.float32)
+        b = rng.standard_normal((h, h)).astype(np.float32) if var == 2 else None
+        g = rng.uniform(0.5, 1.5, h).astype(np.float32) if var == 1 else None
+        be = rng.standard_normal(h).astype(np.float32) if var == 1 else None
+        o, ms = _lib.op_attention(q, k, v, h, var, a, b, g, be, "bf16", iters=iters)
+        out[name] = dict(ms=ms, tflops=4.0 * B * h * n * n * dh / ms / 1e9, crc=zlib.crc32(o.tobytes()))
     elif name == "attention":
         B, n, h = 256, 197, 12
         q, k, v = (rng.standard_normal((B, n, h * 64), dtype=np.float32) for _ in range(3))

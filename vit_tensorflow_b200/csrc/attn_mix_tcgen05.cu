@@ -46,7 +46,7 @@ namespace {
 constexpr int MX_THREADS = 320;            // the register file is allocated per 4 warps: 168 registers per thread
 constexpr int MX_PRODUCER = 8, MX_MMA = 9;
 constexpr int MX_ROWS = 64;                 // query rows per item
-constexpr int MX_KST = 2;                   // key-block ring depth
+constexpr int MX_KSLOTS_BYTES = 64 * 1024;  // key ring at H = 16 (Q takes 128 KB); H = 8 gets 128 KB
 constexpr int MX_MAXNK = 256;               // keys per image the phase-B stage is sized for
 constexpr int MX_QT = 64 * 128;             // Q tile of one head: 64 rows x 128 bytes
 constexpr int MX_KT = 16 * 128;             // key block of one head: 16 keys x 128 bytes
@@ -57,12 +57,18 @@ struct MixW { float wa[H * H], wb[H * H], gamma[H], beta[H]; };
 
 template <int H, bool SPLIT>
 struct MxCfg {
-  static constexpr int A_BYTES = H * MX_QT + MX_KST * H * MX_KT;                          // phase A: Q + key ring
+  // The key ring is a ring of (key block, head) tiles of 2 KB, not of whole key blocks: the issuer frees a tile as soon as
+  // that head's S product retires and the producer refills it at once, so the TMA latency (~2 K cycles) is covered by the 32 / 64
+  // tiles in flight.  (A ring of two whole 16-key blocks left the mixers waiting for S 37 % of the time: ncu source page of the
+  // first build, profiles/r02_ncu_mix_first.md.)
+  static constexpr int KSLOTS = (H <= 8 ? 2 : 1) * MX_KSLOTS_BYTES / MX_KT;
+  static constexpr int A_BYTES = H * MX_QT + KSLOTS * MX_KT;                                // phase A: Q + key-tile ring
   static constexpr int PB_STAGE = (SPLIT ? 2 : 1) * (MX_MAXNK / 8) * 1024 + 2 * MX_VBOX;    // phase B stage: A_g plane(s) + V_g
   static constexpr int B_BYTES = 2 * PB_STAGE;
   static constexpr int DATA = A_BYTES > B_BYTES ? A_BYTES : B_BYTES;
   static constexpr int STAT = 2 * H * 2 * MX_ROWS * 4;                                      // final + exchange tables
-  static constexpr int SMEM = DATA + STAT + 256 + 1024;
+  static constexpr int BARS = 160 + 16 * KSLOTS;
+  static constexpr int SMEM = DATA + STAT + BARS + 1024;
   static_assert(SMEM <= 227 * 1024, "attn_mix: shared memory budget");
 };
 
@@ -94,13 +100,14 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   float* part = stat + H * 2 * MX_ROWS;                          // exchange between the two mixer groups
   const uint32_t bars = base + C::DATA + C::STAT;
   const uint32_t q_full = bars, pa_done = bars + 8, o_full = bars + 16, o_empty = bars + 24;
-  auto k_full = [&](int s) { return bars + 32u + 8u * s; };
-  auto k_empty = [&](int s) { return bars + 48u + 8u * s; };
-  auto s_full = [&](int g) { return bars + 64u + 8u * g; };
-  auto s_empty = [&](int g) { return bars + 80u + 8u * g; };
-  auto pb_full = [&](int s) { return bars + 96u + 8u * s; };
-  auto pb_empty = [&](int s) { return bars + 112u + 8u * s; };
-  const uint32_t tmem_slot = bars + 128u;
+  auto s_full = [&](int g) { return bars + 32u + 8u * g; };
+  auto s_empty = [&](int g) { return bars + 48u + 8u * g; };
+  auto pb_full = [&](int s) { return bars + 64u + 8u * s; };
+  auto pb_empty = [&](int s) { return bars + 80u + 8u * s; };
+  const uint32_t tmem_slot = bars + 96u;
+  auto k_full = [&](uint32_t s) { return bars + 160u + 8u * s; };
+  auto k_empty = [&](uint32_t s) { return bars + 160u + 8u * C::KSLOTS + 8u * s; };
+  constexpr uint32_t KSLOTS = C::KSLOTS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = (nk + 15) >> 4;                               // key blocks of 16
@@ -112,7 +119,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1); mbar_init(pa_done, 8); mbar_init(o_full, 1); mbar_init(o_empty, 8);
-    for (int s = 0; s < MX_KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
+    for (uint32_t s = 0; s < KSLOTS; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
     for (int g = 0; g < 2; ++g) { mbar_init(s_full(g), 1); mbar_init(s_empty(g), 4); mbar_init(pb_full(g), 1); mbar_init(pb_empty(g), 1); }
     fence_mbar_init();
   }
@@ -138,14 +145,16 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       __syncwarp();
       for (int pass = 0; pass < 2; ++pass) {
-        for (int blk = 0; blk < nblk; ++blk, ++kcnt) {
-          const int st = kcnt % MX_KST;
-          mbar_wait(k_empty(st), ((kcnt / MX_KST) & 1u) ^ 1u);
-          if (elect_one()) {
-            mbar_arrive_expect_tx(k_full(st), H * MX_KT);
-            for (int h = 0; h < H; ++h) tma_load_3d(sK + (st * H + h) * MX_KT, &tmap_k, k_full(st), h * dh, blk * 16, b);
+        for (int blk = 0; blk < nblk; ++blk) {
+          for (int h = 0; h < H; ++h, ++kcnt) {
+            const uint32_t st = kcnt % KSLOTS;
+            mbar_wait(k_empty(st), ((kcnt / KSLOTS) & 1u) ^ 1u);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(k_full(st), MX_KT);
+              tma_load_3d(sK + st * MX_KT, &tmap_k, k_full(st), h * dh, blk * 16, b);
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       // ---- phase B: A_g (scratch) + V_g per head
@@ -170,30 +179,32 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ===================================================================== MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(MX_ROWS, 16, 0, 0);
     const uint32_t idesc_pv = make_idesc_bf16(MX_ROWS, dh, 0, 1);        // B (= V) is MN-major
-    uint32_t kcnt = 0, pcnt = 0, n = 0, sfull_cnt[2] = {0, 0};
+    uint32_t kcnt = 0, pcnt = 0, n = 0, sfull_cnt0 = 0, sfull_cnt1 = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
       if (n > 0) mbar_wait(o_empty, (n - 1) & 1u);                 // the previous item's outputs have left tensor memory
       mbar_wait(q_full, n & 1u);
       tcgen05_fence_after();
       for (int pass = 0; pass < 2; ++pass) {
-        for (int blk = 0; blk < nblk; ++blk, ++kcnt) {
-          const int st = kcnt % MX_KST;
+        for (int blk = 0; blk < nblk; ++blk) {
           const int G = (blk >> 1) & 1, p = blk & 1;
-          mbar_wait(k_full(st), (kcnt / MX_KST) & 1u);
-          if (p == 0 && sfull_cnt[G] > 0) mbar_wait(s_empty(G), (sfull_cnt[G] - 1) & 1u);   // group G holds its previous S in registers
-          tcgen05_fence_after();
+          const uint32_t cntG = G ? sfull_cnt1 : sfull_cnt0;
+          if (p == 0 && cntG > 0) mbar_wait(s_empty(G), (cntG - 1) & 1u);   // group G holds its previous S in registers
           const uint32_t d0 = tmem_base + (static_cast<uint32_t>(p * 16) << 16) + G * (H * 16);
-          if (elect_one()) {
-            for (int h = 0; h < H; ++h) {
-              const uint64_t dq = make_smem_desc(sQ + h * MX_QT, 16, 1024, 2);
-              const uint64_t dk = make_smem_desc(sK + (st * H + h) * MX_KT, 16, 1024, 2);
+          const bool last_of_sb = (p == 1 || blk == nblk - 1);
+          for (int h = 0; h < H; ++h, ++kcnt) {
+            const uint32_t st = kcnt % KSLOTS;
+            mbar_wait(k_full(st), (kcnt / KSLOTS) & 1u);
+            tcgen05_fence_after();
+            const uint64_t dq = make_smem_desc(sQ + h * MX_QT, 16, 1024, 2);
+            const uint64_t dk = make_smem_desc(sK + st * MX_KT, 16, 1024, 2);
+            if (elect_one()) {
               for (int ks = 0; ks < ksteps; ++ks) umma_f16_ss(d0 + h * 16, dq + 2u * ks, dk + 2u * ks, idesc_s, ks != 0);
+              umma_commit(k_empty(st));
+              if (last_of_sb && h == H - 1) umma_commit(s_full(G));
             }
-            umma_commit(k_empty(st));
-            if (p == 1 || blk == nblk - 1) umma_commit(s_full(G));
+            __syncwarp();
           }
-          __syncwarp();
-          if (p == 1 || blk == nblk - 1) ++sfull_cnt[G];
+          if (last_of_sb) { if (G) ++sfull_cnt1; else ++sfull_cnt0; }
         }
       }
       // ---- phase B: O_g = A_g V_g
