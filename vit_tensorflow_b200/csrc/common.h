@@ -52,7 +52,7 @@ inline bool first_use_on_this_device(unsigned long long (&seen)[4]) {
 
 // 2-D / 3-D bf16 tensor maps (innermost dimension first), 128-byte swizzle unless swizzle == false.
 CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
-                         uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true);
+                         uint32_t box_inner, uint32_t box_outer, bool swizzle128 = true, bool f32 = false);
 CUtensorMap make_tmap_3d(const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                          uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, bool swizzle128 = true);
 
@@ -64,6 +64,7 @@ struct GemmBf16 {
   int M = 0, N = 0, K = 0;
   __nv_bfloat16* out = nullptr;         // [M, ldc] (the epilogue stores rows straight from registers)
   int ldc = 0;
+  bool out_f32 = false;                 // `out` is float* (ldc in floats): plain / bias epilogue only
   int block_n = 256;
   int cta_group = 2;                    // 2: CTA pairs (cta_group::2) on 256-row tiles; 1: single-CTA 128-row tiles
   const float* bias = nullptr;          // [N] or null
@@ -86,7 +87,7 @@ struct GemmBf16 {
 // lda/ldw/ldc/ldr in elements; all must be multiples of 8 (16-byte TMA strides); N % 64 == 0.
 GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt, int ldw, __nv_bfloat16* out, int ldc,
                         int M, int N, int K, const float* bias, const float* scale, const __nv_bfloat16* res, int ldr,
-                        bool gelu);
+                        bool gelu, bool out_f32 = false, int b_rows = 0);
 void gemm_bf16_run(const GemmBf16& g, cudaStream_t stream);
 bool gemm_bf16_supported(int M, int N, int K, int lda, int ldw, int ldc);
 long long*& gemm_trace_buffer();

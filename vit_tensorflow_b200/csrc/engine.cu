@@ -113,6 +113,7 @@ struct LayerW {                    // one pre-norm transformer layer in any of t
   const float* ff_scale = nullptr;
   int heads = 0, dim_head = 0, variant = 0;   // dim_head: head width of the q/k/v ACTIVATIONS (the padded width when dh_model < it)
   int dh_model = 0;                  // the model's dim_head: softmax scale dh_model^-0.5 (vit.py:57)
+  int t2t_D = 0, t2t_Dp = 0;         // tensor-core T2T soft-split layer: true width D (LayerNorm, softmax scale), padded width Dp
   bool folded = false;               // attn_norm / ff_norm folded into to_qkv (to_q, to_kv) / fc1
 };
 
@@ -399,11 +400,11 @@ struct vb_handle {
   }
   bool has(const std::string& name) const { return windex.count(name) != 0; }
 
-  Linear make_linear(const std::string& n, int K, int N, bool bias = true, const Norm* fold = nullptr) {
+  Linear make_linear(const std::string& n, int K, int N, bool bias = true, const Norm* fold = nullptr, int ldw_min = 0) {
     Linear L;
     L.W = W(n + ".kernel");
     L.bias = bias ? W(n + ".bias") : nullptr;
-    L.K = K; L.N = N; L.ldw = round_up(K, 8);
+    L.K = K; L.N = N; L.ldw = round_up(K, 8) > ldw_min ? round_up(K, 8) : ldw_min;
     if (bf16()) {
       owned.emplace_back(new DevMem());
       owned.back()->ensure(static_cast<size_t>(N) * L.ldw * sizeof(__nv_bfloat16));
@@ -497,6 +498,39 @@ struct vb_handle {
     l.fc2 = make_linear(pre + "fc2", mlp, dim);
     return l;
   }
+  // One-layer transformer between two T2T soft splits (t2t.py:35,45-46: heads = 1, dim_head = mlp_dim = dim = D = channels * prod(k^2),
+  // 147 and 1323 at the default t2t_layers; no out-projection, vit.py:53) on the tensor cores: every width is zero-padded to
+  // Dp = round_up(D, 64) -- token rows [n, Dp] with zero pad columns, to_qkv columns [q | k | v] each Dp wide, fc1 / fc2 Dp x Dp --
+  // so that all four GEMMs and the per-image QK^T / PV products run on the tcgen05 GEMM kernel; LayerNorm and the softmax scale keep
+  // the true D.  Zero weights and biases keep the pad columns exactly zero through the layer (GELU(0) = 0).
+  static bool t2t_tensor_path_enabled() { static const bool off = getenv("VB_NO_T2T_TC") != nullptr; return !off; }
+  LayerW make_t2t_layer(const std::string& pre, int D) {
+    const int Dp = round_up(D, 64);
+    auto padded = [&](const std::string& n, int other, int groups, int pad_rows, const float* src, int dh_src) {
+      owned.emplace_back(new DevMem());
+      owned.back()->ensure(static_cast<size_t>(other) * groups * Dp * sizeof(float));
+      float* wp = static_cast<float*>(owned.back()->p);
+      pad_heads_f32(src, wp, other, groups, 1, dh_src, Dp, pad_rows, 0);
+      woverride[n] = wp;
+      return wp;
+    };
+    padded(pre + "to_qkv.kernel", D, 3, 0, W(pre + "to_qkv.kernel"), D);                    // [D, 3 D] -> [D, 3 Dp]
+    padded(pre + "fc1.kernel", D, 1, 0, W(pre + "fc1.kernel"), D);                          // [D, D] -> [D, Dp]
+    padded(pre + "fc1.bias", 1, 1, 0, W(pre + "fc1.bias"), D);
+    const float* rows_padded = padded(pre + "fc2.kernel", D, 1, 1, W(pre + "fc2.kernel"), D);   // [D, D] -> [Dp, D] (zero input rows)
+    padded(pre + "fc2.kernel", Dp, 1, 0, rows_padded, D);                                   // -> [Dp, Dp]
+    padded(pre + "fc2.bias", 1, 1, 0, W(pre + "fc2.bias"), D);
+    LayerW l;
+    l.heads = 1; l.dim_head = Dp; l.dh_model = D; l.t2t_D = D; l.t2t_Dp = Dp;
+    l.attn_norm = make_norm(pre + "attn_norm", D);
+    l.ff_norm = make_norm(pre + "ff_norm", D);
+    l.fused_qkv = true; l.project_out = false;
+    l.to_qkv = make_linear(pre + "to_qkv", D, 3 * Dp, false, nullptr, Dp);
+    l.fc1 = make_linear(pre + "fc1", D, Dp, true, nullptr, Dp);
+    l.fc2 = make_linear(pre + "fc2", Dp, Dp, true, nullptr, Dp);
+    l.to_qkv.K = Dp; l.fc1.K = Dp;                                                        // the A operands are Dp wide (zero pad columns)
+    return l;
+  }
   EmbedW make_embed(const std::string& pre, int p_h, int p_w, int dim, int n_pos, bool with_cls = true, int K = 0) {
     EmbedW e;
     e.patch = make_linear(pre + "patch", K > 0 ? K : p_h * p_w * cfg.channels, dim);
@@ -539,8 +573,11 @@ struct vb_handle {
       int out = c.image_h;
       for (size_t i = 0; i < st.size(); ++i) {
         out = conv_output_size(out, st[i].k, st[i].stride);
-        if (i + 1 < st.size())
-          t2t_layers.push_back(make_layer("t2t." + std::to_string(i) + ".layers.0.", st[i].dim, 1, st[i].dim, st[i].dim, VB_KIND_VIT, false));
+        if (i + 1 < st.size()) {
+          const std::string pre = "t2t." + std::to_string(i) + ".layers.0.";
+          if (bf16() && t2t_tensor_path_enabled()) t2t_layers.push_back(make_t2t_layer(pre, st[i].dim));
+          else t2t_layers.push_back(make_layer(pre, st[i].dim, 1, st[i].dim, st[i].dim, VB_KIND_VIT, false));
+        }
       }
       embed = make_embed("", 0, 0, c.dim, out * out + 1, true, st.back().dim);
       for (int L = 0; L < c.depth; ++L) layers.push_back(make_layer("layers." + std::to_string(L) + ".", c.dim, c.heads, c.dim_head, c.mlp_dim, VB_KIND_VIT));
@@ -670,27 +707,29 @@ struct vb_handle {
   T* embed_t2t(const float* img, int B, int H, int Wd, int* rows_out, cudaStream_t s, float** stats_out) {
     const auto st = t2t_stages();
     const T* map = nullptr;
-    int mh = H, mw = Wd, mc = cfg.channels;
+    int mh = H, mw = Wd, mc = cfg.channels, map_ld = 0;
     for (size_t i = 0; i < st.size(); ++i) {
       const int oh = (mh + st[i].stride - 1) / st[i].stride, ow = (mw + st[i].stride - 1) / st[i].stride;
       const int D = st[i].dim, n = oh * ow;
       VB_CHECK(i == 0 || mh == mw, "T2TViT: token maps after the first soft split must be square (t2t.py:41)");
       const bool last = i + 1 == st.size();
-      const int ld = last ? (bf16() ? embed.patch.ldw : embed.patch.K) : D;
+      const bool tc = !last && t2t_layers[i].t2t_Dp > 0;               // tensor-core layer: token rows padded to Dp columns
+      const int ld = last ? (bf16() ? embed.patch.ldw : embed.patch.K) : (tc ? t2t_layers[i].t2t_Dp : D);
       const int cls_row = last ? 1 : 0;
       T* out = arena.get<T>(static_cast<size_t>(B) * (n + cls_row) * ld);
       {
         ProfScope ps(this, PROF_EMBED, 0.0, static_cast<double>(i == 0 ? 4 : sizeof(T)) * B * mh * mw * mc + static_cast<double>(sizeof(T)) * B * (n + cls_row) * ld, s);
         if (i == 0) unfold_same<float, T>(img, out, B, mh, mw, mc, st[i].k, st[i].stride, cls_row, ld, s);
-        else unfold_same<T, T>(map, out, B, mh, mw, mc, st[i].k, st[i].stride, cls_row, ld, s);
+        else unfold_same<T, T>(map, out, B, mh, mw, mc, st[i].k, st[i].stride, cls_row, ld, s, map_ld);
       }
       if (last) {
         VB_CHECK(n + 1 <= embed.n_pos, "image has more patches than pos_embedding rows");
         *rows_out = n + 1;
         return embed_from_cols<T>(embed, out, ld, B, n + 1, s, stats_out);
       }
-      layer_self<T>(out, B, n, D, t2t_layers[i], s);
-      map = out; mh = oh; mw = ow; mc = D;
+      if (tc) layer_t2t<T>(out, B, n, t2t_layers[i], s);
+      else layer_self<T>(out, B, n, D, t2t_layers[i], s);
+      map = out; mh = oh; mw = ow; mc = D; map_ld = ld;
     }
     VB_CHECK(false, "T2TViT needs at least one t2t layer");
     return nullptr;
@@ -716,6 +755,34 @@ struct vb_handle {
     attention_dispatch<T>(Q, dim, Y, dim, Y, dim, O, dim, B, nt, rows, 1, dim, 0, nullptr, nullptr, nullptr, nullptr, s);
     return O;
   }
+
+  // tcgen05 GEMM on raw operands through the plan cache (the T2T soft-split attention products)
+  void gemm_cached(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt, int ldw, int b_rows, void* out, int ldc, int M, int N, int K,
+                   const __nv_bfloat16* res, int ldr, bool out_f32, int cls, cudaStream_t s) {
+    ProfScope ps(this, cls, 2.0 * M * N * K, 2.0 * (static_cast<double>(M) * K + static_cast<double>(N) * K) + (out_f32 ? 4.0 : 2.0) * M * N, s);
+    PlanKey key{};
+    const uintptr_t parts[16] = {reinterpret_cast<uintptr_t>(A), static_cast<uintptr_t>(lda), reinterpret_cast<uintptr_t>(Wt),
+                                 reinterpret_cast<uintptr_t>(out), static_cast<uintptr_t>(ldc), static_cast<uintptr_t>(M),
+                                 static_cast<uintptr_t>(N), static_cast<uintptr_t>(K), static_cast<uintptr_t>(ldw),
+                                 static_cast<uintptr_t>(b_rows), reinterpret_cast<uintptr_t>(res), static_cast<uintptr_t>(ldr),
+                                 static_cast<uintptr_t>(out_f32), 0x7247u, 0, 0};
+    for (int i = 0; i < 16; ++i) key[i] = parts[i];
+    auto it = plans.find(key);
+    if (it == plans.end()) {
+      if (plans.size() > 8192) plans.clear();
+      it = plans.emplace(key, gemm_bf16_plan(A, lda, Wt, ldw, static_cast<__nv_bfloat16*>(out), ldc, M, N, K, nullptr, nullptr, res, ldr,
+                                             false, out_f32, b_rows)).first;
+    }
+    gemm_bf16_run(it->second, s);
+  }
+
+  // One T2T soft-split transformer layer on the tensor cores (see make_t2t_layer).  X [B*n, Dp] bf16, zero pad columns, updated
+  // in place.  Attention with ONE head of width D = 147 / 1323 over n = 3136 / 784 tokens (t2t.py:35) does not fit the fused
+  // attention kernels' head widths: per image, S = Q K^T (tcgen05 GEMM, fp32 out), softmax rows -> bf16 P, O = P V (tcgen05 GEMM
+  // against V^T, residual X added in its epilogue).  The score / probability buffers of ONE image (39 + 20 MB at n = 3136) are
+  // reused for every image, so they stay in the 126 MB L2 instead of streaming B x n x n floats through HBM.
+  template <typename T>
+  void layer_t2t(T* X, int B, int n, const LayerW& l, cudaStream_t s);
 
   // one pre-norm layer, self-attention over all rows (vit.py:101-102, cait.py:150-151, cross_vit.py:109-111).
   // `stats` (bf16 engine, folded layers): per-row (sum, sumsq) partials of X, valid on entry iff *stats_valid; the
@@ -1107,6 +1174,39 @@ template <>
 void vb_handle::ensure_stats<__nv_bfloat16>(const __nv_bfloat16* X, int dim, float* stats, int M, cudaStream_t s) {
   ProfScope ps(this, PROF_LN, 0.0, 2.0 * M * dim, s);
   row_stats_bf16(X, dim, stats, M, dim, s);
+}
+
+template <>
+void vb_handle::layer_t2t<float>(float*, int, int, const LayerW&, cudaStream_t) { VB_CHECK(false, "internal: tensor-core T2T layer in the fp32 engine"); }
+template <>
+void vb_handle::layer_t2t<__nv_bfloat16>(__nv_bfloat16* X, int B, int n, const LayerW& l, cudaStream_t s) {
+  using bf = __nv_bfloat16;
+  const int D = l.t2t_D, Dp = l.t2t_Dp, M = B * n, npad = round_up(n, 64);
+  bf* Y = arena.get<bf>(static_cast<size_t>(M) * Dp);
+  bf* QKV = arena.get<bf>(static_cast<size_t>(M) * 3 * Dp);
+  bf* Vt = arena.get<bf>(static_cast<size_t>(B) * Dp * npad);
+  float* S = arena.get<float>(static_cast<size_t>(n) * npad);
+  bf* P = arena.get<bf>(static_cast<size_t>(n) * npad);
+  { ProfScope ps(this, PROF_LN, 0.0, 4.0 * M * D, s); layernorm<bf>(X, Dp, l.attn_norm.gamma, l.attn_norm.beta, Y, Dp, M, D, s, Dp); }
+  linear<bf>(Y, Dp, M, l.to_qkv, QKV, 3 * Dp, Epi(), s);
+  {
+    ProfScope ps(this, PROF_OTHER, 0.0, 4.0 * M * Dp, s);
+    transpose_rows_bf16(QKV + 2 * Dp, 3 * Dp, static_cast<long long>(n) * 3 * Dp, Vt, npad, static_cast<long long>(Dp) * npad, B, n, npad, Dp, s);
+  }
+  const float scale_log2 = (1.0f / sqrtf(static_cast<float>(D))) * 1.4426950408889634f;
+  for (int b = 0; b < B; ++b) {
+    const bf* Qb = QKV + static_cast<size_t>(b) * n * 3 * Dp;
+    bf* Xb = X + static_cast<size_t>(b) * n * Dp;
+    gemm_cached(Qb, 3 * Dp, Qb + Dp, 3 * Dp, n, S, npad, n, npad, Dp, nullptr, 0, true, PROF_ATTN, s);           // S = Q K^T
+    { ProfScope ps(this, PROF_ATTN, 0.0, 6.0 * n * npad, s); softmax_rows_bf16(S, npad, P, npad, n, n, npad, scale_log2, s); }
+    gemm_cached(P, npad, Vt + static_cast<size_t>(b) * Dp * npad, npad, 0, Xb, Dp, n, Dp, npad, Xb, Dp, false, PROF_ATTN, s);   // X += P V
+  }
+  { ProfScope ps(this, PROF_LN, 0.0, 4.0 * M * D, s); layernorm<bf>(X, Dp, l.ff_norm.gamma, l.ff_norm.beta, Y, Dp, M, D, s, Dp); }
+  bf* Hb = arena.get<bf>(static_cast<size_t>(M) * Dp);
+  Epi e1; e1.gelu = true; e1.bias = l.fc1.bias;
+  linear<bf>(Y, Dp, M, l.fc1, Hb, Dp, e1, s);
+  Epi e2; e2.bias = l.fc2.bias; e2.res = X; e2.ldr = Dp;
+  linear<bf>(Hb, Dp, M, l.fc2, X, Dp, e2, s);
 }
 
 template <typename T>

@@ -46,7 +46,9 @@ constexpr int CONST_BYTES = 2048;         // folded LayerNorm: (mean, rstd) of t
 // one (to_qkv, fc1 + GELU -- the LayerNorm-folded, epilogue-heavy GEMMs whose MMA warp measured 4-6 K cycles of tmem_empty
 // wait every other tile with 8 epilogue warps) one slab per warp is enough, so 12 warps (3 per sub-partition) fit beside the
 // same ring; their chunk body runs on 32-column halves to stay inside the 136 registers a 480-thread CTA allows.
-template <int BN, int CG, bool RES>
+// OF32: fp32 output (the T2T soft-split attention scores, softmaxed by a separate kernel): a 64-column chunk is two 128-byte-row
+// slabs of 32 columns, each with its own TMA store through an fp32 tensor map.
+template <int BN, int CG, bool RES, bool OF32 = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CG) * BK * 2;               // each CTA of a pair stages half of B
@@ -60,7 +62,7 @@ struct Cfg {
   static constexpr int NUM_THREADS = (EPI_WARPS + 3) * 32;
   // 4 KB slabs per epilogue warp: residual-in (double-buffered, prefetched one chunk ahead) and, with the TMA-store
   // epilogue, the output staging (shared with the residual slab)
-  static constexpr int SLABS = RES ? 2 : (VB_GEMM_DIRECT_STORE ? 0 : 1);
+  static constexpr int SLABS = (RES || OF32) ? 2 : (VB_GEMM_DIRECT_STORE ? 0 : 1);
   static constexpr bool HALVES = EW >= 3;                           // chunk body on 32-column halves (register diet)
   static constexpr int NUM_STAGING = SLABS * EPI_WARPS;
   static constexpr int STAGES_FIT = (227 * 1024 - NUM_STAGING * STAGING_BYTES - CONST_BYTES - 512 - 1024) / STAGE_BYTES;
@@ -94,14 +96,15 @@ __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
 }
 
 // EPI: 0 = no per-column addend, 1 = + bias[n], 2 = folded LayerNorm (c1 = ln_c1, c2 = bias)
-template <int BN, bool GELU, bool RES, int CG, int EPI>
-__global__ void __launch_bounds__((Cfg<BN, CG, RES>::NUM_THREADS), 1)
+template <int BN, bool GELU, bool RES, int CG, int EPI, bool OF32>
+__global__ void __launch_bounds__((Cfg<BN, CG, RES, OF32>::NUM_THREADS), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_r, int M, int N, int K,
                  __nv_bfloat16* __restrict__ out, int ldc, const float* __restrict__ bias, const float* __restrict__ scale,
                  const __nv_bfloat16* res, int ldr, const float* __restrict__ ln_c1, const float2* ln_stats, int ln_parts,
                  float ln_inv_d, float2* __restrict__ stats_out, int stats_parts, long long* __restrict__ dbg) {
-  using C = Cfg<BN, CG, RES>;
+  using C = Cfg<BN, CG, RES, OF32>;
+  static_assert(!OF32 || (!GELU && !RES && !VB_GEMM_DIRECT_STORE), "fp32 output: plain / bias epilogue only");
   constexpr int PRODUCER_WARP = C::PRODUCER_WARP, MMA_WARP = C::MMA_WARP, STATS_WARP = C::STATS_WARP;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -345,7 +348,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int ncol0 = n0 + cc * 64;
         const bool col_ok = ncol0 < N;                              // N % 64 == 0: a chunk is entirely in or out
         const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + cc * 64;
-        const uint32_t slab = slab0 + (RES ? (cnt & 1u) * 4096 : 0u);
+        const uint32_t slab = slab0 + (RES ? (cnt & 1u) * 4096 : 0u);    // OF32: slab0 = columns 0-31, slab0 + 4096 = columns 32-63
         const uint32_t srow = slab + lane * 128;
         const bool last_of_tile = (kk + EW >= total_chunks) || (static_cast<int>((kk + EW) / CPT) != it);
         // All of this warp's TMEM reads of the accumulator buffer are complete once the last chunk's values sit in registers:
@@ -412,6 +415,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 f[4 * k + 3] = add2(f[4 * k + 3], bf16x2_to_f32x2(w3));
               }
             }
+          }
+          if (OF32) {                                                 // 16 floats = 64 bytes of this row's 128-byte slab row
+            const uint32_t srow32 = slab0 + (g >> 1) * 4096 + lane * 128;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t slot = static_cast<uint32_t>(((g & 1) * 4 + k) ^ (lane & 7));
+              asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(srow32 + slot * 16), "l"(f[2 * k]), "l"(f[2 * k + 1]) : "memory");
+            }
+            return;
           }
           uint32_t pk[8];
 #pragma unroll
@@ -501,7 +513,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            if (col_ok) tma_store_2d(&tmap_c, slab, ncol0, m0 + q * 32);
+            if (col_ok) {
+              tma_store_2d(&tmap_c, slab, ncol0, m0 + q * 32);
+              if (OF32) tma_store_2d(&tmap_c, slab + 4096, ncol0 + 32, m0 + q * 32);
+            }
             bulk_commit_group();
           }
         }
@@ -543,15 +558,15 @@ long long*& gemm_trace_buffer() {   // debugging aid: device trace buffer [4 rol
 }
 namespace {
 
-template <int BN, bool GELU, bool RES, int CG, int EPI>
+template <int BN, bool GELU, bool RES, int CG, int EPI, bool OF32 = false>
 void launch(const GemmBf16& g, cudaStream_t stream) {
-  auto kern = gemm_bf16_kernel<BN, GELU, RES, CG, EPI>;
+  auto kern = gemm_bf16_kernel<BN, GELU, RES, CG, EPI, OF32>;
   static unsigned long long seen[4] = {0, 0, 0, 0};
-  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG, RES>::SMEM_BYTES));
+  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, CG, RES, OF32>::SMEM_BYTES));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.grid);
-  cfg.blockDim = dim3(Cfg<BN, CG, RES>::NUM_THREADS);
-  cfg.dynamicSmemBytes = Cfg<BN, CG, RES>::SMEM_BYTES;
+  cfg.blockDim = dim3(Cfg<BN, CG, RES, OF32>::NUM_THREADS);
+  cfg.dynamicSmemBytes = Cfg<BN, CG, RES, OF32>::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -573,6 +588,11 @@ void launch_epi(const GemmBf16& g, cudaStream_t stream) {
   const bool res = g.res != nullptr;
   const int epi = g.ln_c1 != nullptr ? 2 : g.bias != nullptr ? 1 : 0;
   VB_CHECK(epi != 2 || (g.bias != nullptr && g.ln_stats != nullptr && g.ln_parts > 0), "folded LayerNorm needs c1, c2 and the row statistics");
+  if (g.out_f32) {
+    VB_CHECK(!g.gelu && !res && epi != 2 && g.scale == nullptr && g.stats_out == nullptr, "fp32-output GEMM: plain or bias epilogue only");
+    if (epi == 0) return launch<BN, false, false, CG, 0, true>(g, stream);
+    return launch<BN, false, false, CG, 1, true>(g, stream);
+  }
 #define VB_GEMM_CASE(G, R, E) if (g.gelu == G && res == R && epi == E) return launch<BN, G, R, CG, E>(g, stream)
   VB_GEMM_CASE(false, false, 0); VB_GEMM_CASE(false, false, 1); VB_GEMM_CASE(false, false, 2);
   VB_GEMM_CASE(true, false, 0);  VB_GEMM_CASE(true, false, 1);  VB_GEMM_CASE(true, false, 2);
@@ -594,13 +614,13 @@ int sm_count() {                                  // of the CURRENT device (one 
 }
 
 CUtensorMap make_tmap_2d(const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes, uint32_t box_inner,
-                         uint32_t box_outer, bool swizzle128) {
+                         uint32_t box_outer, bool swizzle128, bool f32) {
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {outer_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = get_encode_fn()(&m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE,
                                swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -628,7 +648,8 @@ bool gemm_bf16_supported(int M, int N, int K, int lda, int ldw, int ldc) {
 }
 
 GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt, int ldw, __nv_bfloat16* out, int ldc, int M,
-                        int N, int K, const float* bias, const float* scale, const __nv_bfloat16* res, int ldr, bool gelu) {
+                        int N, int K, const float* bias, const float* scale, const __nv_bfloat16* res, int ldr, bool gelu,
+                        bool out_f32, int b_rows) {
   VB_CHECK(gemm_bf16_supported(M, N, K, lda, ldw, ldc), "gemm_bf16: unsupported shape (need N%64==0, K%8==0, ld%8==0)");
   VB_CHECK(res == nullptr || ldr % 8 == 0, "gemm_bf16: residual leading dimension must be a multiple of 8");
   VB_CHECK((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Wt) | reinterpret_cast<uintptr_t>(out) |
@@ -636,13 +657,16 @@ GemmBf16 gemm_bf16_plan(const __nv_bfloat16* A, int lda, const __nv_bfloat16* Wt
   GemmBf16 g;
   g.M = M; g.N = N; g.K = K;
   g.bias = bias; g.scale = scale; g.res = res; g.ldr = ldr; g.gelu = gelu;
-  g.out = out; g.ldc = ldc;
+  g.out = out; g.ldc = ldc; g.out_f32 = out_f32;
   // 256-wide tiles unless N only fills 128-wide ones well (e.g. CaiT dim 384) or the problem is tiny.
   g.block_n = (N % 256 == 0 || N >= 1024) ? 256 : 128;
   g.cta_group = (M > BM) ? 2 : 1;      // pair two SMs on 256-row tiles unless the whole problem is one 128-row tile
   g.tmap_a = make_tmap_2d(A, K, M, static_cast<uint64_t>(lda) * 2, BK, BM);
-  g.tmap_b = make_tmap_2d(Wt, K, N, static_cast<uint64_t>(ldw) * 2, BK, g.block_n / g.cta_group);
-  g.tmap_c = make_tmap_2d(out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 32);
+  // b_rows: rows of Wt that exist (< N when the output is column-padded: TMA zero-fills the rest instead of reading on)
+  g.tmap_b = make_tmap_2d(Wt, K, b_rows > 0 ? b_rows : N, static_cast<uint64_t>(ldw) * 2, BK, g.block_n / g.cta_group);
+  // fp32 output: `out` really is a float*, ldc in floats, 32-column (128-byte) boxes
+  g.tmap_c = out_f32 ? make_tmap_2d(out, N, M, static_cast<uint64_t>(ldc) * 4, 32, 32, true, true)
+                     : make_tmap_2d(out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 32);
   g.tmap_r = res ? make_tmap_2d(res, N, M, static_cast<uint64_t>(ldr) * 2, 64, 32) : g.tmap_c;
   const int tm = BM * g.cta_group;
   const int tiles = ((M + tm - 1) / tm) * ((N + g.block_n - 1) / g.block_n);

@@ -186,7 +186,7 @@ __global__ void layernorm_kernel(const T* __restrict__ x, int ldx, const float* 
 // Any D / alignment: one warp per row, three passes over the (L1-resident) row.
 template <typename T>
 __global__ void layernorm_generic_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, T* __restrict__ out, int ldo, int M, int D) {
+                                         const float* __restrict__ beta, T* __restrict__ out, int ldo, int M, int D, int pad_to) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -199,6 +199,93 @@ __global__ void layernorm_generic_kernel(const T* __restrict__ x, int ldx, const
   const float rstd = rsqrtf(warp_sum(sq) / D + 1e-3f);
   T* orow = out + static_cast<long long>(row) * ldo;
   for (int d = lane; d < D; d += 32) orow[d] = from_f<T>((to_f(xr[d]) - mean) * rstd * gamma[d] + beta[d]);
+  for (int d = D + lane; d < pad_to; d += 32) orow[d] = from_f<T>(0.f);     // zero pad columns [D, pad_to) (pitch-padded token rows)
+}
+
+// Row softmax of materialised fp32 scores -> bf16 probabilities (the T2T soft-split attention, t2t.py:35: one head of width
+// 147 / 1323 over 3136 / 784 tokens, far outside the fused kernels' head widths).  One block per row, the row in registers;
+// S holds q.k (unscaled), scale_log2 = dim_head^-0.5 * log2(e); columns [n, npad) of P are zeroed (the PV GEMM's K padding).
+constexpr int SM_THREADS = 256, SM_MAXE = 16;
+__global__ void __launch_bounds__(SM_THREADS)
+softmax_rows_bf16_kernel(const float* __restrict__ S, int lds, __nv_bfloat16* __restrict__ P, int ldp, int n, int npad, float scale_log2) {
+  __shared__ float red[SM_THREADS / 32];
+  const long long row = blockIdx.x;
+  const float* sr = S + row * lds;
+  float v[SM_MAXE];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < SM_MAXE; ++i) {
+    const int e = threadIdx.x + SM_THREADS * i;
+    v[i] = e < n ? sr[e] * scale_log2 : -INFINITY;
+    m = fmaxf(m, v[i]);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w = 1; w < SM_THREADS / 32; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < SM_MAXE; ++i) { v[i] = exp2f(v[i] - m); l += v[i]; }
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+  __syncthreads();
+  l = 0.f;
+#pragma unroll
+  for (int w = 0; w < SM_THREADS / 32; ++w) l += red[w];
+  const float il = 1.0f / l;
+  __nv_bfloat16* pr = P + row * ldp;
+#pragma unroll
+  for (int i = 0; i < SM_MAXE; ++i) {
+    const int e = threadIdx.x + SM_THREADS * i;
+    if (e < npad) pr[e] = __float2bfloat16_rn(e < n ? v[i] * il : 0.f);
+  }
+}
+
+// any row length: three passes over the (L2-resident) row
+__global__ void __launch_bounds__(SM_THREADS)
+softmax_rows_bf16_big_kernel(const float* __restrict__ S, int lds, __nv_bfloat16* __restrict__ P, int ldp, int n, int npad, float scale_log2) {
+  __shared__ float red[SM_THREADS / 32];
+  const long long row = blockIdx.x;
+  const float* sr = S + row * lds;
+  float m = -INFINITY;
+  for (int e = threadIdx.x; e < n; e += SM_THREADS) m = fmaxf(m, sr[e] * scale_log2);
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < SM_THREADS / 32; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float l = 0.f;
+  for (int e = threadIdx.x; e < n; e += SM_THREADS) l += exp2f(sr[e] * scale_log2 - m);
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+  __syncthreads();
+  l = 0.f;
+  for (int w = 0; w < SM_THREADS / 32; ++w) l += red[w];
+  const float il = 1.0f / l;
+  __nv_bfloat16* pr = P + row * ldp;
+  for (int e = threadIdx.x; e < npad; e += SM_THREADS) pr[e] = __float2bfloat16_rn(e < n ? exp2f(sr[e] * scale_log2 - m) * il : 0.f);
+}
+
+// out[b, c, j] = in[b, j, c] (bf16), c < cols, j < npad with zeros for j >= n: V -> V^T for the K-major B operand of the PV GEMM
+__global__ void transpose_rows_bf16_kernel(const __nv_bfloat16* __restrict__ in, int ldi, long long in_batch, __nv_bfloat16* __restrict__ out,
+                                           int ldo, long long out_batch, int n, int npad, int cols) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  const int b = blockIdx.z, j0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const __nv_bfloat16* ib = in + b * in_batch;
+  __nv_bfloat16* ob = out + b * out_batch;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int j = j0 + r, c = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (j < n && c < cols) ? ib[static_cast<long long>(j) * ldi + c] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r, j = j0 + threadIdx.x;
+    if (c < cols && j < npad) ob[static_cast<long long>(c) * ldo + j] = tile[threadIdx.x][r];
+  }
 }
 
 // ------------------------------------------------------------------------------------------ SIMT GEMM
@@ -473,7 +560,7 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ vec, T* __restri
 // 'b h w c -> b (h w) c' (:44).  One thread per output element; taps outside the image read 0; the patch vector is
 // (k_row, k_col, channel) with the channel fastest, so consecutive threads read consecutive channels of one input pixel.
 template <typename TI, typename TO>
-__global__ void unfold_same_kernel(const TI* __restrict__ in, TO* __restrict__ out, int B, int H, int W, int C, int k, int stride,
+__global__ void unfold_same_kernel(const TI* __restrict__ in, int ldi, TO* __restrict__ out, int B, int H, int W, int C, int k, int stride,
                                    int oh, int ow, int pad_top, int pad_left, int cls_row, int ldo) {
   const int rows = cls_row + oh * ow;
   const int K = k * k * C;
@@ -490,7 +577,7 @@ __global__ void unfold_same_kernel(const TI* __restrict__ in, TO* __restrict__ o
       const int oy = p / ow, ox = p % ow;
       const int c = col % C, kx = (col / C) % k, ky = col / (C * k);
       const int y = oy * stride + ky - pad_top, x = ox * stride + kx - pad_left;
-      if (y >= 0 && y < H && x >= 0 && x < W) v = to_f(in[((b * H + y) * W + x) * C + c]);
+      if (y >= 0 && y < H && x >= 0 && x < W) v = to_f(in[((b * H + y) * W + x) * ldi + c]);
     }
     out[idx] = from_f<TO>(v);
   }
@@ -625,6 +712,20 @@ void im2col(const float* img, T* out, int B, int H, int W, int C, int ph, int pw
   VB_LAUNCHED();
 }
 
+void softmax_rows_bf16(const float* S, int lds, __nv_bfloat16* P, int ldp, long long rows, int n, int npad, float scale_log2, cudaStream_t s) {
+  VB_CHECK(n <= npad, "softmax_rows_bf16: n <= npad");
+  if (npad <= SM_THREADS * SM_MAXE) softmax_rows_bf16_kernel<<<static_cast<unsigned>(rows), SM_THREADS, 0, s>>>(S, lds, P, ldp, n, npad, scale_log2);
+  else softmax_rows_bf16_big_kernel<<<static_cast<unsigned>(rows), SM_THREADS, 0, s>>>(S, lds, P, ldp, n, npad, scale_log2);
+  VB_LAUNCHED();
+}
+
+void transpose_rows_bf16(const __nv_bfloat16* in, int ldi, long long in_batch, __nv_bfloat16* out, int ldo, long long out_batch, int B,
+                         int n, int npad, int cols, cudaStream_t s) {
+  dim3 grid((npad + 31) / 32, (cols + 31) / 32, B);
+  transpose_rows_bf16_kernel<<<grid, dim3(32, 8), 0, s>>>(in, ldi, in_batch, out, ldo, out_batch, n, npad, cols);
+  VB_LAUNCHED();
+}
+
 void pad_heads_f32(const float* W, float* Wp, int other, int groups, int heads, int dh, int dhp, int pad_rows, cudaStream_t s) {
   const long long total = static_cast<long long>(other) * groups * heads * dhp;
   pad_heads_kernel<<<grid_1d(total), 256, 0, s>>>(W, Wp, other, groups, heads, dh, dhp, pad_rows);
@@ -640,10 +741,10 @@ void build_embed_residual(T* R, const float* pos, const float* cls, const float*
 }
 
 template <typename T>
-void layernorm(const T* x, int ldx, const float* gamma, const float* beta, T* out, int ldo, int M, int D, cudaStream_t s) {
+void layernorm(const T* x, int ldx, const float* gamma, const float* beta, T* out, int ldo, int M, int D, cudaStream_t s, int pad_to) {
   const int warps = 8;
   const int blocks = (M + warps - 1) / warps;
-  const bool aligned = (D % 8 == 0) && (ldx % 8 == 0) && (ldo % 8 == 0) &&
+  const bool aligned = (pad_to <= D) && (D % 8 == 0) && (ldx % 8 == 0) && (ldo % 8 == 0) &&
                        (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0) &&
                        (reinterpret_cast<uintptr_t>(gamma) % 16 == 0) && (reinterpret_cast<uintptr_t>(beta) % 16 == 0);
   if (aligned && D <= 8 * 32 * 2) {
@@ -651,7 +752,7 @@ void layernorm(const T* x, int ldx, const float* gamma, const float* beta, T* ou
   } else if (aligned && D <= 8 * 32 * 4) {
     layernorm_kernel<T, 4><<<blocks, warps * 32, 0, s>>>(x, ldx, gamma, beta, out, ldo, M, D);
   } else {
-    layernorm_generic_kernel<T><<<blocks, warps * 32, 0, s>>>(x, ldx, gamma, beta, out, ldo, M, D);
+    layernorm_generic_kernel<T><<<blocks, warps * 32, 0, s>>>(x, ldx, gamma, beta, out, ldo, M, D, pad_to);
   }
   VB_LAUNCHED();
 }
@@ -726,11 +827,12 @@ void broadcast_rows(const float* vec, T* dst, int B, int nt, int D, cudaStream_t
 }
 
 template <typename TI, typename TO>
-void unfold_same(const TI* in, TO* out, int B, int H, int W, int C, int k, int stride, int cls_row, int ldo, cudaStream_t s) {
+void unfold_same(const TI* in, TO* out, int B, int H, int W, int C, int k, int stride, int cls_row, int ldo, cudaStream_t s, int ldi) {
+  if (ldi <= 0) ldi = C;
   const int oh = (H + stride - 1) / stride, ow = (W + stride - 1) / stride;
   const int ph = (oh - 1) * stride + k > H ? (oh - 1) * stride + k - H : 0, pw = (ow - 1) * stride + k > W ? (ow - 1) * stride + k - W : 0;
   const long long total = static_cast<long long>(B) * (cls_row + oh * ow) * ldo;
-  unfold_same_kernel<TI, TO><<<grid_1d(total), 256, 0, s>>>(in, out, B, H, W, C, k, stride, oh, ow, ph / 2, pw / 2, cls_row, ldo);
+  unfold_same_kernel<TI, TO><<<grid_1d(total), 256, 0, s>>>(in, ldi, out, B, H, W, C, k, stride, oh, ow, ph / 2, pw / 2, cls_row, ldo);
   VB_LAUNCHED();
 }
 
@@ -777,14 +879,14 @@ void row_stats_bf16(const __nv_bfloat16* X, int ldx, float* stats, int M, int D,
 #define VB_INST_T(T)                                                                                                         \
   template void im2col<T>(const float*, T*, int, int, int, int, int, int, int, int, cudaStream_t);                          \
   template void build_embed_residual<T>(T*, const float*, const float*, const float*, int, int, int, int, cudaStream_t);    \
-  template void layernorm<T>(const T*, int, const float*, const float*, T*, int, int, int, cudaStream_t);                   \
+  template void layernorm<T>(const T*, int, const float*, const float*, T*, int, int, int, cudaStream_t, int);                   \
   template void attn_scores<T>(const T*, int, const T*, int, float*, int, int, int, int, int, float, cudaStream_t);         \
   template void attn_pv<T>(const float*, const T*, int, T*, int, int, int, int, int, int, cudaStream_t);                    \
   template void pool_layernorm<T>(const T*, int, int, const float*, const float*, float*, int, int, int, cudaStream_t);     \
   template void copy_tokens<T>(const T*, int, int, T*, int, int, int, int, int, cudaStream_t);                              \
   template void broadcast_row<T>(const float*, T*, int, int, int, cudaStream_t);                                            \
   template void broadcast_rows<T>(const float*, T*, int, int, int, cudaStream_t);                                           \
-  template void unfold_same<float, T>(const float*, T*, int, int, int, int, int, int, int, int, cudaStream_t);              \
+  template void unfold_same<float, T>(const float*, T*, int, int, int, int, int, int, int, int, cudaStream_t, int);         \
   template void convert_rows<float, T>(const float*, int, T*, int, long long, int, cudaStream_t);
 VB_INST_T(float)
 VB_INST_T(__nv_bfloat16)
@@ -795,7 +897,7 @@ template void gemm_simt<__nv_bfloat16, __nv_bfloat16, __nv_bfloat16>(const __nv_
                                                                      __nv_bfloat16*, int, int, int, int, const float*,
                                                                      const float*, const __nv_bfloat16*, int, int, cudaStream_t);
 template void unfold_same<__nv_bfloat16, __nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, int, int, int, int, int,
-                                                        cudaStream_t);
+                                                        cudaStream_t, int);
 template void convert_rows<__nv_bfloat16, float>(const __nv_bfloat16*, int, float*, int, long long, int, cudaStream_t);
 template void convert<float, __nv_bfloat16>(const float*, __nv_bfloat16*, long long, cudaStream_t);
 template void convert<__nv_bfloat16, float>(const __nv_bfloat16*, float*, long long, cudaStream_t);

@@ -18,8 +18,16 @@ void build_embed_residual(T* R, const float* pos, const float* cls, const float*
                           int has_cls, cudaStream_t s);
 
 // LayerNorm over the last axis (Keras: eps 1e-3, biased variance; vit.py:18).  x [M, ldx] -> out [M, ldo].
+// pad_to > D: columns [D, pad_to) of every output row are zeroed (pitch-padded token rows feeding a K-padded GEMM).
 template <typename T>
-void layernorm(const T* x, int ldx, const float* gamma, const float* beta, T* out, int ldo, int M, int D, cudaStream_t s);
+void layernorm(const T* x, int ldx, const float* gamma, const float* beta, T* out, int ldo, int M, int D, cudaStream_t s, int pad_to = 0);
+
+// Row softmax of materialised fp32 scores -> bf16 probabilities: P[r, j] = softmax_j(S[r, j] * scale), j < n; P[r, n..npad) = 0.
+// scale_log2 = scale * log2(e).  Rows of up to 4096 keys stay in registers; longer rows take a three-pass kernel.
+void softmax_rows_bf16(const float* S, int lds, __nv_bfloat16* P, int ldp, long long rows, int n, int npad, float scale_log2, cudaStream_t s);
+// out[b, c, j] = in[b, j, c] for c < cols, j < n; out[b, c, n..npad) = 0 (bf16; batch pitches in elements)
+void transpose_rows_bf16(const __nv_bfloat16* in, int ldi, long long in_batch, __nv_bfloat16* out, int ldo, long long out_batch, int B,
+                         int n, int npad, int cols, cudaStream_t s);
 
 // out[M,N] (TO) = epi(A[M,K] (TA, lda) x W), W element (k,n) at W[k*wsk + n*wsn]; fp32 FMA accumulation.
 // epi = (+bias) -> GELU(erf) -> (*scale) -> (+res[m*ldr + n]).
@@ -58,8 +66,9 @@ void broadcast_rows(const float* vec, T* dst, int B, int nt, int D, cudaStream_t
 // T2T soft split (t2t.py:43-44): tf.image.extract_patches(sizes k, strides `stride`, rates 1, padding SAME) +
 // 'b h w c -> b (h w) c'.  in [B,H,W,C] (image or token map) -> out [B*(cls_row + oh*ow), ldo], oh = ceil(H/stride);
 // columns [0, k*k*C) hold the patch vector ((k_row, k_col, c), c fastest), [.., ldo) and the optional cls row are zero.
+// ldi: pitch of one input pixel's channel vector (0 = C).
 template <typename TI, typename TO>
-void unfold_same(const TI* in, TO* out, int B, int H, int W, int C, int k, int stride, int cls_row, int ldo, cudaStream_t s);
+void unfold_same(const TI* in, TO* out, int B, int H, int W, int C, int k, int stride, int cls_row, int ldo, cudaStream_t s, int ldi = 0);
 
 // out[r, 0:cols] = in[r, 0:cols], out[r, cols:ldo] = 0 (type conversion with a row-pitch change).
 template <typename TI, typename TO>
