@@ -57,12 +57,13 @@ struct MixW { float wa[H * H], wb[H * H], gamma[H], beta[H]; };
 
 template <int H, bool SPLIT>
 struct MxCfg {
-  // The key ring is a ring of (key block, head) tiles of 2 KB, not of whole key blocks: the issuer frees a tile as soon as
-  // that head's S product retires and the producer refills it at once, so the TMA latency (~2 K cycles) is covered by the 32 / 64
-  // tiles in flight.  (A ring of two whole 16-key blocks left the mixers waiting for S 37 % of the time: ncu source page of the
-  // first build, profiles/r02_ncu_mix_first.md.)
-  static constexpr int KSLOTS = (H <= 8 ? 2 : 1) * MX_KSLOTS_BYTES / MX_KT;
-  static constexpr int A_BYTES = H * MX_QT + KSLOTS * MX_KT;                                // phase A: Q + key-tile ring
+  // Key ring: whole 16-key blocks (all heads, H x 2 KB), as deep as shared memory allows beside Q: 8 blocks at H = 8, 2 at
+  // H = 16 (Q alone is 128 KB there).  With 2 blocks at H = 8 the mixers waited for S 37 % of the time (ncu source page of the
+  // first build, profiles/r02_ncu_mix.md: one block per ~1 K cycles of TMA round trip against ~0.6 K of mixing); a ring of
+  // single (block, head) tiles was worse still -- 16 / 32 barrier round trips per block on the issuer's critical path
+  // (mix_cait 210 -> 298 us, profiles/r02_ab_mix.txt).
+  static constexpr int KSLOTS = (H <= 8 ? 2 : 1) * MX_KSLOTS_BYTES / (H * MX_KT);
+  static constexpr int A_BYTES = H * MX_QT + KSLOTS * H * MX_KT;                            // phase A: Q + key-block ring
   static constexpr int PB_STAGE = (SPLIT ? 2 : 1) * (MX_MAXNK / 8) * 1024 + 2 * MX_VBOX;    // phase B stage: A_g plane(s) + V_g
   static constexpr int B_BYTES = 2 * PB_STAGE;
   static constexpr int DATA = A_BYTES > B_BYTES ? A_BYTES : B_BYTES;
@@ -120,7 +121,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1); mbar_init(pa_done, 8); mbar_init(o_full, 1); mbar_init(o_empty, 8);
     for (uint32_t s = 0; s < KSLOTS; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
-    for (int g = 0; g < 2; ++g) { mbar_init(s_full(g), 1); mbar_init(s_empty(g), 4); mbar_init(pb_full(g), 1); mbar_init(pb_empty(g), 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(s_full(g), 1); mbar_init(s_empty(g), 8); mbar_init(pb_full(g), 1); mbar_init(pb_empty(g), 1); }
     fence_mbar_init();
   }
   if (warp == MX_MMA) tmem_alloc<512>(tmem_slot);
@@ -145,16 +146,14 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       __syncwarp();
       for (int pass = 0; pass < 2; ++pass) {
-        for (int blk = 0; blk < nblk; ++blk) {
-          for (int h = 0; h < H; ++h, ++kcnt) {
-            const uint32_t st = kcnt % KSLOTS;
-            mbar_wait(k_empty(st), ((kcnt / KSLOTS) & 1u) ^ 1u);
-            if (elect_one()) {
-              mbar_arrive_expect_tx(k_full(st), MX_KT);
-              tma_load_3d(sK + st * MX_KT, &tmap_k, k_full(st), h * dh, blk * 16, b);
-            }
-            __syncwarp();
+        for (int blk = 0; blk < nblk; ++blk, ++kcnt) {
+          const uint32_t st = kcnt % KSLOTS;
+          mbar_wait(k_empty(st), ((kcnt / KSLOTS) & 1u) ^ 1u);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(k_full(st), H * MX_KT);
+            for (int h = 0; h < H; ++h) tma_load_3d(sK + (st * H + h) * MX_KT, &tmap_k, k_full(st), h * dh, blk * 16, b);
           }
+          __syncwarp();
         }
       }
       // ---- phase B: A_g (scratch) + V_g per head
@@ -179,32 +178,35 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // ===================================================================== MMA issuer
     constexpr uint32_t idesc_s = make_idesc_bf16(MX_ROWS, 16, 0, 0);
     const uint32_t idesc_pv = make_idesc_bf16(MX_ROWS, dh, 0, 1);        // B (= V) is MN-major
-    uint32_t kcnt = 0, pcnt = 0, n = 0, sfull_cnt0 = 0, sfull_cnt1 = 0;
+    uint32_t kcnt = 0, pcnt = 0, n = 0, sbc = 0;                   // sbc: super-blocks issued so far (S buffer = sbc & 1)
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
       if (n > 0) mbar_wait(o_empty, (n - 1) & 1u);                 // the previous item's outputs have left tensor memory
       mbar_wait(q_full, n & 1u);
       tcgen05_fence_after();
       for (int pass = 0; pass < 2; ++pass) {
-        for (int blk = 0; blk < nblk; ++blk) {
-          const int G = (blk >> 1) & 1, p = blk & 1;
-          const uint32_t cntG = G ? sfull_cnt1 : sfull_cnt0;
-          if (p == 0 && cntG > 0) mbar_wait(s_empty(G), (cntG - 1) & 1u);   // group G holds its previous S in registers
+        for (int blk = 0; blk < nblk; ++blk, ++kcnt) {
+          // Both mixer groups work on the SAME super-block (group 0: key quarters 0, 1 of each block; group 1: quarters 2, 3),
+          // so the two S column sets double-buffer: super-block sb + 1 is multiplied while sb is being mixed.
+          const int G = static_cast<int>(sbc & 1u), p = blk & 1;
+          const uint32_t st = kcnt % KSLOTS;
+          mbar_wait(k_full(st), (kcnt / KSLOTS) & 1u);
+          if (p == 0 && sbc >= 2) mbar_wait(s_empty(G), ((sbc >> 1) - 1) & 1u);   // all eight mixer warps have read buffer G
+          tcgen05_fence_after();
           const uint32_t d0 = tmem_base + (static_cast<uint32_t>(p * 16) << 16) + G * (H * 16);
           const bool last_of_sb = (p == 1 || blk == nblk - 1);
-          for (int h = 0; h < H; ++h, ++kcnt) {
-            const uint32_t st = kcnt % KSLOTS;
-            mbar_wait(k_full(st), (kcnt / KSLOTS) & 1u);
-            tcgen05_fence_after();
-            const uint64_t dq = make_smem_desc(sQ + h * MX_QT, 16, 1024, 2);
-            const uint64_t dk = make_smem_desc(sK + st * MX_KT, 16, 1024, 2);
-            if (elect_one()) {
+          const uint64_t dq0 = make_smem_desc(sQ, 16, 1024, 2);
+          const uint64_t dk0 = make_smem_desc(sK + st * H * MX_KT, 16, 1024, 2);
+          if (elect_one()) {
+#pragma unroll 4
+            for (int h = 0; h < H; ++h) {
+              const uint64_t dq = dq0 + static_cast<uint32_t>(h * (MX_QT >> 4)), dk = dk0 + static_cast<uint32_t>(h * (MX_KT >> 4));
               for (int ks = 0; ks < ksteps; ++ks) umma_f16_ss(d0 + h * 16, dq + 2u * ks, dk + 2u * ks, idesc_s, ks != 0);
-              umma_commit(k_empty(st));
-              if (last_of_sb && h == H - 1) umma_commit(s_full(G));
             }
-            __syncwarp();
+            umma_commit(k_empty(st));
+            if (last_of_sb) umma_commit(s_full(G));
           }
-          if (last_of_sb) { if (G) ++sfull_cnt1; else ++sfull_cnt0; }
+          __syncwarp();
+          if (last_of_sb) ++sbc;
         }
       }
       // ---- phase B: O_g = A_g V_g
@@ -236,8 +238,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const int G = warp >> 2, q = warp & 3;
     const int row = q * 16 + (lane & 15), par = lane >> 4;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);   // this warp's lane quarter (thread -> lane q*32 + lane)
-    const uint32_t tS = t_lane + G * (H * 16);
-    uint32_t sfull_cnt = 0, n = 0;
+    uint32_t sbc = 0, n = 0;                                         // super-blocks consumed so far (S buffer = sbc & 1)
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
       const int b = it % B, q0 = (it / B) * MX_ROWS;
       const bool active = q * 16 < nq - q0;                        // a warp whose 16 rows all lie past nq only keeps the protocol
@@ -245,14 +246,15 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
       for (int h = 0; h < H; ++h) { m_run[h] = -INFINITY; l_run[h] = 0.f; }
       for (int pass = 0; pass < 2; ++pass) {
-        for (int sb = G; sb < nsb; sb += 2) {
-          mbar_wait(s_full(G), sfull_cnt & 1u);
-          ++sfull_cnt;
+        for (int sb = 0; sb < nsb; ++sb, ++sbc) {
+          const int buf = static_cast<int>(sbc & 1u);
+          const uint32_t tS = t_lane + buf * (H * 16);
+          mbar_wait(s_full(buf), (sbc >> 1) & 1u);
           tcgen05_fence_after();
           const int blk = 2 * sb + par;
           const bool blk_ok = blk < nblk;
 #pragma unroll 1
-          for (int r = 0; r < 4; ++r) {                            // quarters of 4 keys
+          for (int r = 2 * G; r < 2 * G + 2; ++r) {                // this group's two quarters of 4 keys
             float x[H][4];
             if (active) {
 #pragma unroll
@@ -264,10 +266,10 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               }
               tmem_ld_wait();
             }
-            if (r == 3) {                                          // last read of this super-block's S columns
+            if (r == 2 * G + 1) {                                  // this warp's last read of the super-block's S columns
               tcgen05_fence_before();
               __syncwarp();
-              if (lane == 0) mbar_arrive(s_empty(G));
+              if (lane == 0) mbar_arrive(s_empty(buf));
             }
             if (!active || !blk_ok) continue;
             const int key0 = blk * 16 + r * 4;
@@ -509,7 +511,11 @@ bool attention_mix(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int 
   const CUtensorMap tk = make_tmap_3d(k, inner, nk, B, static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(nk) * ldk * 2, 64, 16, 1);
   const CUtensorMap tv = make_tmap_3d(v, inner, nk, B, static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(nk) * ldv * 2, 64, 128, 1);
   const float scale_log2 = (scale > 0.f ? scale : 1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
-  const bool split = variant == 1 && getenv("VB_ATTN_MIX_NOSPLIT") == nullptr;
+  // DeepViT's post-LayerNorm attention weights are O(1) with mixed signs (not probabilities).  One bf16 plane (2^-9 relative, like
+  // every other activation of the engine) measured the same end-to-end error as hi + lo planes at DeepViT-24 (max |err| 0.037 /
+  // 0.039 vs 0.038 / 0.044 on logits of std 1, profiles/r02_config_size_parity.json) at half the scratch traffic: the second
+  // plane is opt-in (VB_ATTN_MIX_SPLIT=1).
+  const bool split = variant == 1 && getenv("VB_ATTN_MIX_SPLIT") != nullptr;
   if (heads == 8) {
     if (variant == 2) launch_mix<8, 2, false>(tq, tk, tv, P, out, ldo, B, nq, nk, dh, scale_log2, s);
     else if (split) launch_mix<8, 1, true>(tq, tk, tv, P, out, ldo, B, nq, nk, dh, scale_log2, s);
