@@ -49,7 +49,10 @@ constexpr int MX_ROWS = 64;                 // query rows per item
 constexpr int MX_KSLOTS_BYTES = 64 * 1024;  // key ring at H = 16 (Q takes 128 KB); H = 8 gets 128 KB
 constexpr int MX_MAXNK = 256;               // keys per image the phase-B stage is sized for
 constexpr int MX_QT = 64 * 128;             // Q tile of one head: 64 rows x 128 bytes
-constexpr int MX_KT = 16 * 128;             // key block of one head: 16 keys x 128 bytes
+// Keys per block = N of the S products.  A tcgen05.mma costs the issuer ~100 cycles however small it is (M = 64 reads its A
+// operand from shared memory per instruction): at N = 16 the 48 (H = 8) / 128 (H = 16) products of a super-block paced the whole
+// kernel (ncu: mixers waiting on s_full 15-19 %).  H = 8 has the tensor-memory columns for N = 32 (2 x 8 x 32 = 512).
+template <int H> struct MxKB { static constexpr int value = H <= 8 ? 32 : 16; };
 constexpr int MX_VBOX = 128 * 128;          // V box: 128 keys x 128 bytes
 
 template <int H>
@@ -62,8 +65,10 @@ struct MxCfg {
   // first build, profiles/r02_ncu_mix.md: one block per ~1 K cycles of TMA round trip against ~0.6 K of mixing); a ring of
   // single (block, head) tiles was worse still -- 16 / 32 barrier round trips per block on the issuer's critical path
   // (mix_cait 210 -> 298 us, profiles/r02_ab_mix.txt).
-  static constexpr int KSLOTS = (H <= 8 ? 2 : 1) * MX_KSLOTS_BYTES / (H * MX_KT);
-  static constexpr int A_BYTES = H * MX_QT + KSLOTS * H * MX_KT;                            // phase A: Q + key-block ring
+  static constexpr int KB = MxKB<H>::value;
+  static constexpr int KT = KB * 128;                                                       // key block of one head: KB keys x 128 bytes
+  static constexpr int KSLOTS = (H <= 8 ? 2 : 1) * MX_KSLOTS_BYTES / (H * KT);
+  static constexpr int A_BYTES = H * MX_QT + KSLOTS * H * KT;                               // phase A: Q + key-block ring
   static constexpr int PB_STAGE = (SPLIT ? 2 : 1) * (MX_MAXNK / 8) * 1024 + 2 * MX_VBOX;    // phase B stage: A_g plane(s) + V_g
   static constexpr int B_BYTES = 2 * PB_STAGE;
   static constexpr int DATA = A_BYTES > B_BYTES ? A_BYTES : B_BYTES;
@@ -90,6 +95,11 @@ __global__ void __launch_bounds__(MX_THREADS, 1)
 attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ MixW<H> W, __nv_bfloat16* __restrict__ out, int ldo,
                 uint8_t* __restrict__ scratch, long long slot_bytes, int B, int nq, int nk, int dh, int num_items, float scale_log2) {
+  // Item order: image-major -- the tiles of one image are adjacent items, i.e. run on neighbouring CTAs at the same time, so
+  // the image's K and V are read from HBM once and served to the other tiles (and to both softmax passes) by the L2; the tile
+  // index is rotated by the image index so that a CTA's static stride over the items does not always hit the same (e.g. the
+  // short last) tile.  (Tile-major order measured 3.6x the algorithmic DRAM traffic at DeepViT-24: ncu, profiles/r02_ncu_mix.md.)
+  const int tiles = (nq + MX_ROWS - 1) / MX_ROWS;
   using C = MxCfg<H, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -111,9 +121,11 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   constexpr uint32_t KSLOTS = C::KSLOTS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nblk = (nk + 15) >> 4;                               // key blocks of 16
+  constexpr int KB = C::KB, MX_KT = C::KT, QPB = KB / 4;         // keys per block, bytes per (block, head) tile, 4-key quarters per block
+  const int nblk = (nk + KB - 1) / KB;                           // key blocks
   const int nsb = (nblk + 1) >> 1;                               // super-blocks (pairs of key blocks sharing S columns)
-  const int nkg = 2 * nblk;                                      // 8-key groups in the scratch layout
+  const int nk16 = (nk + 15) >> 4;                               // 16-key steps of the PV products
+  const int nkg = 2 * nk16;                                      // 8-key groups in the scratch layout
   const int ksteps = dh >> 4;
   const uint32_t plane_bytes = static_cast<uint32_t>(H) * nkg * 1024u;
   uint8_t* slot = scratch + static_cast<long long>(blockIdx.x) * slot_bytes;
@@ -138,7 +150,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); }
     uint32_t kcnt = 0, pcnt = 0, n = 0;
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
-      const int b = it % B, q0 = (it / B) * MX_ROWS;
+      const int b = it / tiles, q0 = ((it + b) % tiles) * MX_ROWS;   // see item order below
       if (n > 0) mbar_wait(o_full, (n - 1) & 1u);                  // every PV product of the previous item has read its stage
       if (elect_one()) {
         mbar_arrive_expect_tx(q_full, H * MX_QT);
@@ -151,7 +163,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(k_empty(st), ((kcnt / KSLOTS) & 1u) ^ 1u);
           if (elect_one()) {
             mbar_arrive_expect_tx(k_full(st), H * MX_KT);
-            for (int h = 0; h < H; ++h) tma_load_3d(sK + (st * H + h) * MX_KT, &tmap_k, k_full(st), h * dh, blk * 16, b);
+            for (int h = 0; h < H; ++h) tma_load_3d(sK + (st * H + h) * MX_KT, &tmap_k, k_full(st), h * dh, blk * KB, b);
           }
           __syncwarp();
         }
@@ -176,7 +188,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
   } else if (warp == MX_MMA) {
     // ===================================================================== MMA issuer
-    constexpr uint32_t idesc_s = make_idesc_bf16(MX_ROWS, 16, 0, 0);
+    constexpr uint32_t idesc_s = make_idesc_bf16(MX_ROWS, KB, 0, 0);
     const uint32_t idesc_pv = make_idesc_bf16(MX_ROWS, dh, 0, 1);        // B (= V) is MN-major
     uint32_t kcnt = 0, pcnt = 0, n = 0, sbc = 0;                   // sbc: super-blocks issued so far (S buffer = sbc & 1)
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
@@ -192,7 +204,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(k_full(st), (kcnt / KSLOTS) & 1u);
           if (p == 0 && sbc >= 2) mbar_wait(s_empty(G), ((sbc >> 1) - 1) & 1u);   // all eight mixer warps have read buffer G
           tcgen05_fence_after();
-          const uint32_t d0 = tmem_base + (static_cast<uint32_t>(p * 16) << 16) + G * (H * 16);
+          const uint32_t d0 = tmem_base + (static_cast<uint32_t>(p * 16) << 16) + G * (H * KB);
           const bool last_of_sb = (p == 1 || blk == nblk - 1);
           const uint64_t dq0 = make_smem_desc(sQ, 16, 1024, 2);
           const uint64_t dk0 = make_smem_desc(sK + st * H * MX_KT, 16, 1024, 2);
@@ -200,7 +212,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll 4
             for (int h = 0; h < H; ++h) {
               const uint64_t dq = dq0 + static_cast<uint32_t>(h * (MX_QT >> 4)), dk = dk0 + static_cast<uint32_t>(h * (MX_KT >> 4));
-              for (int ks = 0; ks < ksteps; ++ks) umma_f16_ss(d0 + h * 16, dq + 2u * ks, dk + 2u * ks, idesc_s, ks != 0);
+              for (int ks = 0; ks < ksteps; ++ks) umma_f16_ss(d0 + h * KB, dq + 2u * ks, dk + 2u * ks, idesc_s, ks != 0);
             }
             umma_commit(k_empty(st));
             if (last_of_sb) umma_commit(s_full(G));
@@ -223,7 +235,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint64_t dl = make_smem_desc(sA + (MX_MAXNK / 8) * 1024, 1024, 128, 0);
         const uint64_t dv = make_smem_desc(sV, 8192, 1024, 2);
         if (elect_one()) {
-          for (int ks = 0; ks < nblk; ++ks) {
+          for (int ks = 0; ks < nk16; ++ks) {
             umma_f16_ss(dO, da + ks * 128u, dv + ks * 128u, idesc_pv, ks != 0);
             if (SPLIT) umma_f16_ss(dO, dl + ks * 128u, dv + ks * 128u, idesc_pv, 1u);
           }
@@ -240,7 +252,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);   // this warp's lane quarter (thread -> lane q*32 + lane)
     uint32_t sbc = 0, n = 0;                                         // super-blocks consumed so far (S buffer = sbc & 1)
     for (int it = blockIdx.x; it < num_items; it += gridDim.x, ++n) {
-      const int b = it % B, q0 = (it / B) * MX_ROWS;
+      const int b = it / tiles, q0 = ((it + b) % tiles) * MX_ROWS;   // see item order below
       const bool active = q * 16 < nq - q0;                        // a warp whose 16 rows all lie past nq only keeps the protocol
       float m_run[H], l_run[H];
 #pragma unroll
@@ -248,49 +260,53 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       for (int pass = 0; pass < 2; ++pass) {
         for (int sb = 0; sb < nsb; ++sb, ++sbc) {
           const int buf = static_cast<int>(sbc & 1u);
-          const uint32_t tS = t_lane + buf * (H * 16);
+          const uint32_t tS = t_lane + buf * (H * KB);
           mbar_wait(s_full(buf), (sbc >> 1) & 1u);
           tcgen05_fence_after();
           const int blk = 2 * sb + par;
           const bool blk_ok = blk < nblk;
 #pragma unroll 1
-          for (int r = 2 * G; r < 2 * G + 2; ++r) {                // this group's two quarters of 4 keys
+          for (int r = G * (QPB / 2); r < (G + 1) * (QPB / 2); ++r) {   // this group's half of the block's 4-key quarters
             float x[H][4];
             if (active) {
 #pragma unroll
               for (int h = 0; h < H; ++h) {
                 uint32_t v[4];
-                tmem_ld_32x32b_x4(tS + h * 16 + r * 4, v);
+                tmem_ld_32x32b_x4(tS + h * KB + r * 4, v);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) x[h][j] = __uint_as_float(v[j]);
               }
               tmem_ld_wait();
             }
-            if (r == 2 * G + 1) {                                  // this warp's last read of the super-block's S columns
+            if (r == (G + 1) * (QPB / 2) - 1) {                    // this warp's last read of the super-block's S columns
               tcgen05_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(s_empty(buf));
             }
-            if (!active || !blk_ok) continue;
-            const int key0 = blk * 16 + r * 4;
+            const int key0 = blk * KB + r * 4;
+            if (!active || !blk_ok || key0 >= nk16 * 16) continue;   // past the last 16-key step: neither scored nor multiplied
             const int nvalid = nk - key0;                          // keys [key0, key0 + 4) below nk
 #pragma unroll
             for (int h = 0; h < H; ++h)
 #pragma unroll
               for (int j = 0; j < 4; ++j) x[h][j] *= scale_log2;
             if (VARIANT == 2) {                                    // cait.py:123: dots <- einsum(dots, mix_heads_pre_attn) (linear: commutes with the scale)
+              // packed over PAIRS OF OUTPUT HEADS: FFMA2 takes the weight pair (W[h][2g], W[h][2g+1]) from a uniform-register
+              // pair (LDCU from the kernel parameters) and the score as a broadcast scalar operand -- half the instructions of
+              // the scalar form, no packing moves
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                float y[H];
+                f32x2 y2[H / 2];
 #pragma unroll
-                for (int g = 0; g < H; ++g) {
-                  float a = 0.f;
+                for (int gp = 0; gp < H / 2; ++gp) y2[gp] = 0ull;
 #pragma unroll
-                  for (int h = 0; h < H; ++h) a = fmaf(W.wa[h * H + g], x[h][j], a);
-                  y[g] = a;
+                for (int h = 0; h < H; ++h) {
+                  const f32x2 xs = splat2(x[h][j]);
+#pragma unroll
+                  for (int gp = 0; gp < H / 2; ++gp) y2[gp] = fma2(pack2(W.wa[h * H + 2 * gp], W.wa[h * H + 2 * gp + 1]), xs, y2[gp]);
                 }
 #pragma unroll
-                for (int g = 0; g < H; ++g) x[g][j] = y[g];
+                for (int gp = 0; gp < H / 2; ++gp) unpack2(y2[gp], x[2 * gp][j], x[2 * gp + 1][j]);
               }
             }
             if (nvalid < 4) {
@@ -322,33 +338,47 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               uint32_t nh[H][2], nl[SPLIT ? H : 1][2];
 #pragma unroll
               for (int jp = 0; jp < 2; ++jp) {                     // key pairs (2 jp, 2 jp + 1)
-                float a0[H], a1[H];
+                // the mix of keys (2 jp, 2 jp + 1), packed over pairs of output heads (see the pre-softmax mix above)
+                f32x2 b0[H / 2], b1[H / 2];
 #pragma unroll
-                for (int g = 0; g < H; ++g) {
-                  float c0 = 0.f, c1 = 0.f;
+                for (int gp = 0; gp < H / 2; ++gp) { b0[gp] = 0ull; b1[gp] = 0ull; }
 #pragma unroll
-                  for (int h = 0; h < H; ++h) {
-                    const float w = (VARIANT == 2) ? W.wb[h * H + g] : W.wa[h * H + g];
-                    c0 = fmaf(w, x[h][2 * jp], c0);
-                    c1 = fmaf(w, x[h][2 * jp + 1], c1);
+                for (int h = 0; h < H; ++h) {
+                  const f32x2 x0 = splat2(x[h][2 * jp]), x1 = splat2(x[h][2 * jp + 1]);
+#pragma unroll
+                  for (int gp = 0; gp < H / 2; ++gp) {
+                    const f32x2 w2 = (VARIANT == 2) ? pack2(W.wb[h * H + 2 * gp], W.wb[h * H + 2 * gp + 1])
+                                                    : pack2(W.wa[h * H + 2 * gp], W.wa[h * H + 2 * gp + 1]);
+                    b0[gp] = fma2(w2, x0, b0[gp]);
+                    b1[gp] = fma2(w2, x1, b1[gp]);
                   }
-                  a0[g] = c0; a1[g] = c1;
                 }
                 if (VARIANT == 1) {                                // deepvit.py:84: LayerNorm over the head axis, eps 1e-3
-                  float s0 = 0.f, s1 = 0.f;
+                  f32x2 s0 = 0ull, s1 = 0ull;
 #pragma unroll
-                  for (int g = 0; g < H; ++g) { s0 += a0[g]; s1 += a1[g]; }
-                  const float mu0 = s0 * (1.0f / H), mu1 = s1 * (1.0f / H);
-                  float v0 = 0.f, v1 = 0.f;
+                  for (int gp = 0; gp < H / 2; ++gp) { s0 = add2(s0, b0[gp]); s1 = add2(s1, b1[gp]); }
+                  float t0, t1, t2, t3;
+                  unpack2(s0, t0, t1); unpack2(s1, t2, t3);
+                  const float mu0 = (t0 + t1) * (1.0f / H), mu1 = (t2 + t3) * (1.0f / H);
+                  const f32x2 nm0 = splat2(-mu0), nm1 = splat2(-mu1);
+                  f32x2 v0 = 0ull, v1 = 0ull;
 #pragma unroll
-                  for (int g = 0; g < H; ++g) { const float d0 = a0[g] - mu0, d1 = a1[g] - mu1; v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1); }
-                  const float r0 = rsqrtf(v0 * (1.0f / H) + 1e-3f), r1 = rsqrtf(v1 * (1.0f / H) + 1e-3f);
+                  for (int gp = 0; gp < H / 2; ++gp) {
+                    b0[gp] = add2(b0[gp], nm0); b1[gp] = add2(b1[gp], nm1);
+                    v0 = fma2(b0[gp], b0[gp], v0); v1 = fma2(b1[gp], b1[gp], v1);
+                  }
+                  unpack2(v0, t0, t1); unpack2(v1, t2, t3);
+                  const f32x2 r0 = splat2(rsqrtf((t0 + t1) * (1.0f / H) + 1e-3f)), r1 = splat2(rsqrtf((t2 + t3) * (1.0f / H) + 1e-3f));
 #pragma unroll
-                  for (int g = 0; g < H; ++g) {
-                    a0[g] = fmaf((a0[g] - mu0) * r0, W.gamma[g], W.beta[g]);
-                    a1[g] = fmaf((a1[g] - mu1) * r1, W.gamma[g], W.beta[g]);
+                  for (int gp = 0; gp < H / 2; ++gp) {
+                    const f32x2 g2 = pack2(W.gamma[2 * gp], W.gamma[2 * gp + 1]), be2 = pack2(W.beta[2 * gp], W.beta[2 * gp + 1]);
+                    b0[gp] = fma2(mul2(b0[gp], r0), g2, be2);
+                    b1[gp] = fma2(mul2(b1[gp], r1), g2, be2);
                   }
                 }
+                float a0[H], a1[H];
+#pragma unroll
+                for (int gp = 0; gp < H / 2; ++gp) { unpack2(b0[gp], a0[2 * gp], a0[2 * gp + 1]); unpack2(b1[gp], a1[2 * gp], a1[2 * gp + 1]); }
 #pragma unroll
                 for (int g = 0; g < H; ++g) {
                   const uint32_t hb = pack_bf16x2(a0[g], a1[g]);
@@ -356,7 +386,7 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                   if (SPLIT) nl[g][jp] = pack_bf16x2(a0[g] - bf16_lo(hb), a1[g] - bf16_hi(hb));
                 }
               }
-              const int kg = blk * 2 + (r >> 1);
+              const int kg = blk * (KB / 8) + (r >> 1);
               uint8_t* dst = slot + (static_cast<size_t>(kg) * MX_ROWS + row) * 16;
               // 8 bytes per head (and plane) and quarter: holding a quarter back for 16-byte stores costs 2 x H registers
               // that the 168-register budget (320 threads) does not have at H = 16; the slot is L2-resident either way
@@ -459,8 +489,8 @@ void launch_mix(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   const int num_items = B * tiles;
   const int nsm = sm_count();
   const int grid = num_items < nsm ? num_items : nsm;
-  const int nblk = (nk + 15) / 16;
-  const long long slot_bytes = static_cast<long long>(SPLIT ? 2 : 1) * H * (2 * nblk) * 1024;
+  const int nk16 = (nk + 15) / 16;
+  const long long slot_bytes = static_cast<long long>(SPLIT ? 2 : 1) * H * (2 * nk16) * 1024;
   int dev = 0;
   VB_CUDA(cudaGetDevice(&dev));
   void* scratch = nullptr;
@@ -508,7 +538,8 @@ bool attention_mix(const __nv_bfloat16* q, int ldq, const __nv_bfloat16* k, int 
   // 3-D maps over (columns, rows of one image, image): rows past n are zero-filled instead of bleeding into the next image;
   // boxes are 64 columns wide whatever dh is (the columns past a head's dh are never multiplied)
   const CUtensorMap tq = make_tmap_3d(q, inner, nq, B, static_cast<uint64_t>(ldq) * 2, static_cast<uint64_t>(nq) * ldq * 2, 64, MX_ROWS, 1);
-  const CUtensorMap tk = make_tmap_3d(k, inner, nk, B, static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(nk) * ldk * 2, 64, 16, 1);
+  const CUtensorMap tk = make_tmap_3d(k, inner, nk, B, static_cast<uint64_t>(ldk) * 2, static_cast<uint64_t>(nk) * ldk * 2, 64,
+                                      heads == 8 ? MxKB<8>::value : MxKB<16>::value, 1);
   const CUtensorMap tv = make_tmap_3d(v, inner, nk, B, static_cast<uint64_t>(ldv) * 2, static_cast<uint64_t>(nk) * ldv * 2, 64, 128, 1);
   const float scale_log2 = (scale > 0.f ? scale : 1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
   // DeepViT's post-LayerNorm attention weights are O(1) with mixed signs (not probabilities).  One bf16 plane (2^-9 relative, like

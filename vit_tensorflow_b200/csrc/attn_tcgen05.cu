@@ -61,6 +61,9 @@ constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_
 // profiles/r02_ab_attn_poly.txt, ViT-B/16 B = 256 shapes, one box): mask 0x0 117.2 us, 0x8 (25 %) 116.4 us, 0xA (50 %) 121.2 us,
 // 0xE (75 %) 131.6 us -- the kernel is not MUFU-bound (nor issue-bound: ~1400 warp instructions per sub-partition and item in
 // 10.4 K cycles); the serial S -> softmax -> P -> PV round trips of the two warps per sub-partition are.  Default: off.
+#ifndef VB_ATTN_COND_LD
+#define VB_ATTN_COND_LD 1
+#endif
 #ifndef VB_ATTN_PINGPONG
 #define VB_ATTN_PINGPONG 1
 #endif
@@ -283,9 +286,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // the only TMEM read of S: this row's 128 scores
         uint32_t v0[32], v1[32], v2[32], v3[32];
         tmem_ld_32x32b_x32(tS, v0);                                       // 32-key chunks past `valid` are never read: the TMEM ->
-        if (valid > 32) tmem_ld_32x32b_x32(tS + 32, v1);                  // register path (64 B/clk/SM) is as scarce as the MUFU
-        if (valid > 64) tmem_ld_32x32b_x32(tS + 64, v2);
-        if (valid > 96) tmem_ld_32x32b_x32(tS + 96, v3);
+        if (!VB_ATTN_COND_LD || valid > 32) tmem_ld_32x32b_x32(tS + 32, v1);   // register path (64 B/clk/SM) is as scarce as the MUFU
+        if (!VB_ATTN_COND_LD || valid > 64) tmem_ld_32x32b_x32(tS + 64, v2);
+        if (!VB_ATTN_COND_LD || valid > 96) tmem_ld_32x32b_x32(tS + 96, v3);
         tmem_ld_wait();
         tcgen05_fence_before();
         __syncwarp();
