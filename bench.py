@@ -126,13 +126,16 @@ def ncu_dram_traffic(config):
     """DRAM bytes (read + write) per GEMM launch from the committed ncu capture of this bench command, or None.
     The number is from a profiler run (cold caches, serialised kernels); it is reported next to the live timing, never
     measured inside it."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", f"r01_dram_traffic_{config}.json")
-    try:
-        with open(path) as fh:
-            d = json.load(fh)
-        return d["gemm_class"]["dram_bytes_per_launch"], os.path.relpath(path, os.path.dirname(os.path.abspath(__file__)))
-    except (OSError, KeyError, ValueError):
-        return None, None
+    root = os.path.dirname(os.path.abspath(__file__))
+    for rnd in ("r02", "r01"):                      # newest committed capture first
+        path = os.path.join(root, "profiles", f"{rnd}_dram_traffic_{config}.json")
+        try:
+            with open(path) as fh:
+                d = json.load(fh)
+            return d["gemm_class"]["dram_bytes_per_launch"], os.path.relpath(path, root)
+        except (OSError, KeyError, ValueError):
+            continue
+    return None, None
 
 
 def usable_cores():
@@ -316,6 +319,9 @@ def run_ours(args, c):
                     launches=g["launches"], avg_launch_ms=g["ms"] / g["launches"],
                     share_of_step=g["ms"] / ms_profiled, profiled_ms_per_step=ms_profiled / args.steps,
                     end_to_end_frac=(value / world) * flops_img / 1e12 / peak,
+                    # the same two fractions against the BURST cuBLAS figure (a kernel timed alone, not under the power cap)
+                    frac_of_burst=achieved / peaks["bf16_tflops"],
+                    end_to_end_frac_of_burst=(value / world) * flops_img / 1e12 / peaks["bf16_tflops"],
                     by_epilogue={k: dict(ms_per_step=prof[k]["ms"] / args.steps, launches_per_step=prof[k]["launches"] / args.steps,
                                          tflops=prof[k]["flops"] / (prof[k]["ms"] * 1e-3) / 1e12)
                                  for k in gemm_classes if prof[k]["launches"]},

@@ -62,7 +62,7 @@ constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_
 // 0xE (75 %) 131.6 us -- the kernel is not MUFU-bound (nor issue-bound: ~1400 warp instructions per sub-partition and item in
 // 10.4 K cycles); the serial S -> softmax -> P -> PV round trips of the two warps per sub-partition are.  Default: off.
 #ifndef VB_ATTN_COND_LD
-#define VB_ATTN_COND_LD 1
+#define VB_ATTN_COND_LD 0            // 1: skip TMEM loads of 32-key chunks past `valid` (measured slower: 36 more spilled registers)
 #endif
 #ifndef VB_ATTN_PINGPONG
 #define VB_ATTN_PINGPONG 1
@@ -274,7 +274,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int h = bh % heads, b = bh / heads;
       const int q0 = pair * 2 * BQ + t * BQ;
       if (q0 >= nq) continue;                                             // this item has a single tile
-      const bool pingpong = VB_ATTN_PINGPONG && (pair * 2 * BQ + BQ < nq);  // both tiles of the item exist
+      // both tiles of the item exist, and at most two key blocks: measured (profiles/r02_ab_attn_variants.txt, one box) 114.3 vs
+      // 117.5 us at n = 197 (2 blocks) but 132.1 vs 122.1 us at n = 577 (5 blocks, where the token serialises more than it de-phases)
+      const bool pingpong = VB_ATTN_PINGPONG && (pair * 2 * BQ + BQ < nq) && nblk <= 2;
       float m_ref = -INFINITY, l_run = 0.f;
       for (int j = 0; j < nblk; ++j) {
         const int valid = min(BKV, nk - j * BKV);
