@@ -278,6 +278,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       // 117.5 us at n = 197 (2 blocks) but 132.1 vs 122.1 us at n = 577 (5 blocks, where the token serialises more than it de-phases)
       const bool pingpong = VB_ATTN_PINGPONG && (pair * 2 * BQ + BQ < nq) && nblk <= 2;
       float m_ref = -INFINITY, l_run = 0.f;
+      // (Letting a warp whose 32 rows all lie past nq -- rows 96-127 of every second tile at n = 197 -- skip its TMEM reads and
+      //  exponentials and only keep the barrier protocol measured SLOWER: 118.6 vs 113.5 us, profiles/r02_ab_attn_deadwarp_skip.txt.)
       for (int j = 0; j < nblk; ++j) {
         const int valid = min(BKV, nk - j * BKV);
         if (wq == 0 && lane == 0) trace(1 + t, 10 + j);
