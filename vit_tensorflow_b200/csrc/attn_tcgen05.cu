@@ -44,10 +44,20 @@ constexpr int BKV = 128;         // keys per block
 constexpr int KV_ST = VB_ATTN_KV_ST;   // K/V ring depth (3: 193 KB of shared memory, 4: 225 KB)
 constexpr int TILE_BYTES = 128 * 128;        // 128 rows x 64 bf16
 constexpr int P_BYTES = 2 * TILE_BYTES;      // 128 rows x 128 keys bf16 as two 64-column swizzled blocks
-constexpr int ATT_THREADS = 384;             // warps 0-3 / 4-7 softmax of tile 0 / 1, warp 8 TMA, warps 10-11 MMA issuers
-constexpr int ATT_PRODUCER_WARP = 8, ATT_MMA_WARP0 = 10;   // issue arbiter favours high warp ids: issuers on top
+// KS = false: 8 softmax warps (warps 0-3 / 4-7 = tile 0 / 1, thread = query row, all 128 keys of a block).
+// KS = true ("key split"): 16 softmax warps -- two per (tile, TMEM lane quarter), each taking two of the block's four 32-key
+// chunks (chunks hf and hf + 2), i.e. FOUR warps per sub-partition whose TMEM-load, MUFU and FP32 phases overlap instead of two
+// running them one after the other; the two threads of a row exchange their half row max (and, once per item, their half row
+// sum) through shared memory and a 64-thread named barrier.  Then: the TMA producer warp, a spare, the two MMA issuers.
+template <bool KS>
+struct AttCfg {
+  static constexpr int NSOFT = KS ? 16 : 8;
+  static constexpr int PRODUCER_WARP = NSOFT, MMA_WARP0 = NSOFT + 2;   // issue arbiter favours high warp ids: issuers on top
+  static constexpr int THREADS = (NSOFT + 4) * 32;
+};
 constexpr int SMEM_DATA = 2 * TILE_BYTES /*Q*/ + KV_ST * 2 * TILE_BYTES /*K,V*/ + 2 * P_BYTES;
-constexpr int ATT_SMEM = SMEM_DATA + 256 + 1024;
+constexpr int XCH_BYTES = 3 * 2 * 2 * 128 * 4;     // KS: exchange slots [row max (2 block parities) | row sum][tile][half][row]
+constexpr int ATT_SMEM = SMEM_DATA + XCH_BYTES + 256 + 1024;
 constexpr int TMEM_COLS_ATT = 512;
 constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_PV + 64 t
 
@@ -61,6 +71,9 @@ constexpr int TM_S = 0, TM_PV = 256;         // S_t at TM_S + 128 t, PV_t at TM_
 // profiles/r02_ab_attn_poly.txt, ViT-B/16 B = 256 shapes, one box): mask 0x0 117.2 us, 0x8 (25 %) 116.4 us, 0xA (50 %) 121.2 us,
 // 0xE (75 %) 131.6 us -- the kernel is not MUFU-bound (nor issue-bound: ~1400 warp instructions per sub-partition and item in
 // 10.4 K cycles); the serial S -> softmax -> P -> PV round trips of the two warps per sub-partition are.  Default: off.
+#ifndef VB_ATTN_KEYSPLIT
+#define VB_ATTN_KEYSPLIT 0                 // default form of the kernel (env VB_ATTN_KEYSPLIT / VB_ATTN_NO_KEYSPLIT flips it)
+#endif
 #ifndef VB_ATTN_COND_LD
 #define VB_ATTN_COND_LD 0            // 1: skip TMEM loads of 32-key chunks past `valid` (measured slower: 36 more spilled registers)
 #endif
@@ -85,7 +98,8 @@ __device__ __forceinline__ f32x2 ex2_poly2(f32x2 t) {
   return pack2u(lo, hi);
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+template <bool KS>
+__global__ void __launch_bounds__(AttCfg<KS>::THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_o, int heads, int nq, int nk,
                 int num_items, float scale_log2, long long* __restrict__ dbg) {
@@ -95,7 +109,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t sK = sQ + 2 * TILE_BYTES;
   const uint32_t sV = sK + KV_ST * TILE_BYTES;
   const uint32_t sP = sV + KV_ST * TILE_BYTES;
-  const uint32_t bars = sP + 2 * P_BYTES;
+  constexpr int ATT_PRODUCER_WARP = AttCfg<KS>::PRODUCER_WARP, ATT_MMA_WARP0 = AttCfg<KS>::MMA_WARP0;
+  const uint32_t sX = sP + 2 * P_BYTES;                          // KS exchange slots
+  const uint32_t bars = sX + XCH_BYTES;
   auto q_full = [&](int t) { return bars + 8u * t; };
   auto q_empty = [&](int t) { return bars + 16u + 8u * t; };
   auto s_full = [&](int t) { return bars + 32u + 8u * t; };
@@ -113,8 +129,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (threadIdx.x == 0) {
     for (int t = 0; t < 2; ++t) {
       mbar_init(q_full(t), 1); mbar_init(q_empty(t), 1);
-      mbar_init(s_full(t), 1); mbar_init(s_empty(t), 4);
-      mbar_init(p_full(t), 4); mbar_init(pv_full(t), 1);
+      mbar_init(s_full(t), 1); mbar_init(s_empty(t), AttCfg<KS>::NSOFT / 2);
+      mbar_init(p_full(t), AttCfg<KS>::NSOFT / 2); mbar_init(pv_full(t), 1);
     }
     for (int s = 0; s < KV_ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 2); }   // one release per tile issuer
     fence_mbar_init();
@@ -258,6 +274,184 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         cur = nxt;
       }
     }
+  } else if (KS) {
+    // ===================================================================== softmax, key-split form (2 warps per tile and lane quarter)
+    if (warp >= 16) goto done;              // spare warp
+    const int t = warp >> 3, hf = (warp >> 2) & 1, wq = warp & 3;
+    const int row_local = wq * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t tS = lane_addr + TM_S + t * 128, tPV = lane_addr + TM_PV + t * 64 + hf * 32;
+    const uint32_t sPt = sP + t * P_BYTES + row_local * 128;
+    const uint32_t pair_bar = 1 + t * 4 + wq;                 // named barrier of the two warps that share these 32 rows
+    auto xslot = [&](int buf, int half) { return sX + static_cast<uint32_t>(((buf * 2 + t) * 2 + half) * 128 + row_local) * 4u; };
+    uint32_t sc = 0, pvc = 0;
+    for (int it = blockIdx.x; it < num_items; it += gridDim.x) {
+      const int pair = it % pairs, bh = it / pairs;
+      const int h = bh % heads, b = bh / heads;
+      const int q0 = pair * 2 * BQ + t * BQ;
+      if (q0 >= nq) continue;                                             // this item has a single tile
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < nblk; ++j) {
+        const int valid = min(BKV, nk - j * BKV);
+        mbar_wait(s_full(t), sc & 1u);
+        ++sc;
+        tcgen05_fence_after();
+        uint32_t va[32], vb[32];                                          // chunks hf and hf + 2 of this row's 128 scores
+        tmem_ld_32x32b_x32(tS + hf * 32, va);
+        tmem_ld_32x32b_x32(tS + (hf + 2) * 32, vb);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty(t));
+        auto chunk_max = [&](int c, const uint32_t (&v)[32]) -> float {
+          const int nv = valid - c * 32;
+          float a = -INFINITY, b2 = -INFINITY;
+          if (nv >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              a = fmaxf(a, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
+              b2 = fmaxf(b2, fmaxf(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])));
+            }
+          } else if (nv > 0) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              a = (i < nv) ? fmaxf(a, __uint_as_float(v[i])) : a;
+              b2 = (i + 1 < nv) ? fmaxf(b2, __uint_as_float(v[i + 1])) : b2;
+            }
+          }
+          return fmaxf(a, b2);
+        };
+        float mx = fmaxf(chunk_max(hf, va), chunk_max(hf + 2, vb));
+        if (j == 0 && hf == 0) {                                          // previous item's output slab (same bytes as P) drained
+          if (lane == 0) bulk_wait_group_read<0>();
+          __syncwarp();
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xslot(j & 1, hf)), "f"(mx) : "memory");
+        named_bar_sync(pair_bar, 64);
+        {
+          float mo;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mo) : "r"(xslot(j & 1, hf ^ 1)) : "memory");
+          mx = fmaxf(mx, mo);
+        }
+        const float m_blk = mx * scale_log2;
+        float alpha = 1.0f;
+        const bool need = m_blk > m_ref + 8.0f;                           // identical in both threads of the row
+        if (need) { alpha = ex2_approx(m_ref - m_blk); m_ref = m_blk; l_run *= alpha; }
+        if (j > 0) {
+          mbar_wait(pv_full(t), pvc & 1u);
+          ++pvc;
+          if (__any_sync(0xffffffffu, need)) {                            // each half rescales its 32 output columns
+            tcgen05_fence_after();
+            const f32x2 a2 = splat2(alpha);
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint32_t ov[16];
+              tmem_ld_32x32b_x16(tPV + g * 16, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float x0, x1;
+                unpack2(mul2(pack2u(ov[2 * i], ov[2 * i + 1]), a2), x0, x1);
+                ov[2 * i] = __float_as_uint(x0);
+                ov[2 * i + 1] = __float_as_uint(x1);
+              }
+              tmem_st_32x32b_x16(tPV + g * 16, ov);
+            }
+            tmem_st_wait();
+          }
+        }
+        f32x2 rsum2 = 0ull;
+        const f32x2 sc2 = splat2(scale_log2), nm2 = splat2(-m_ref);
+        auto emit = [&](int c, const uint32_t (&v)[32]) {                 // chunk c = keys [32c, 32c+32) of the block
+          const int nv = valid - c * 32;
+          if (nv <= 0) return;
+          const uint32_t rowp = sPt + (c >> 1) * TILE_BYTES;
+          if (nv >= 32) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int e = k * 8 + 2 * i;
+                float x0, x1;
+                unpack2(fma2(pack2u(v[e], v[e + 1]), sc2, nm2), x0, x1);
+                const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                rsum2 = add2(rsum2, pack2(p0, p1));
+                pk[i] = pack_bf16x2(p0, p1);
+              }
+              const uint32_t slot = static_cast<uint32_t>(((c & 1) * 4 + k) ^ (row_local & 7));
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                           "r"(pk[3]) : "memory");
+            }
+            return;
+          }
+          const int nv16 = (nv + 15) & ~15;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (k * 8 >= nv16) break;
+            uint32_t pk[4] = {0u, 0u, 0u, 0u};
+            if (k * 8 < nv) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int e = k * 8 + 2 * i;
+                float x0, x1;
+                unpack2(fma2(pack2u(v[e], v[e + 1]), sc2, nm2), x0, x1);
+                const float p0 = (e < nv) ? ex2_approx(x0) : 0.f;
+                const float p1 = (e + 1 < nv) ? ex2_approx(x1) : 0.f;
+                rsum2 = add2(rsum2, pack2(p0, p1));
+                pk[i] = pack_bf16x2(p0, p1);
+              }
+            }
+            const uint32_t slot = static_cast<uint32_t>(((c & 1) * 4 + k) ^ (row_local & 7));
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                         "r"(pk[3]) : "memory");
+          }
+        };
+        emit(hf, va);
+        emit(hf + 2, vb);
+        float rs0, rs1;
+        unpack2(rsum2, rs0, rs1);
+        l_run += rs0 + rs1;
+        tcgen05_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full(t));
+      }
+      mbar_wait(pv_full(t), pvc & 1u);
+      ++pvc;
+      tcgen05_fence_after();
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(xslot(2, hf)), "f"(l_run) : "memory");
+      named_bar_sync(pair_bar, 64);
+      float lo;
+      asm volatile("ld.shared.f32 %0, [%1];" : "=f"(lo) : "r"(xslot(2, hf ^ 1)) : "memory");
+      const f32x2 il2 = splat2(1.0f / (l_run + lo));
+      {
+        uint32_t oa[32];                                                   // this half's 32 output columns
+        tmem_ld_32x32b_x32(tPV, oa);
+        tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int d = k * 4 + i;
+            pk[i] = pack_bf16x2_from(mul2(pack2u(oa[2 * d], oa[2 * d + 1]), il2));
+          }
+          const uint32_t slot = static_cast<uint32_t>((hf * 4 + k) ^ (row_local & 7));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sPt + slot * 16), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]),
+                       "r"(pk[3]) : "memory");
+        }
+      }
+      tcgen05_fence_before();
+      fence_proxy_async_smem();
+      named_bar_sync(pair_bar, 64);                                       // both halves of the 32 rows are in the slab
+      if (hf == 0 && lane == 0) {
+        tma_store_3d(&tmap_o, sP + t * P_BYTES + wq * 4096, h * DH, q0 + wq * 32, b);
+        bulk_commit_group();
+      }
+      __syncwarp();
+    }
+    if (hf == 0 && lane == 0) bulk_wait_group_read<0>();
   } else {
     // ===================================================================== softmax groups (4 warps per tile)
     if (warp >= 8) goto done;               // spare warp 9
@@ -502,7 +696,17 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
        reinterpret_cast<uintptr_t>(out)) % 16) return false;
   static unsigned long long seen[4] = {0, 0, 0, 0};
-  if (first_use_on_this_device(seen)) VB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  // Form of the kernel.  Measured on one box (profiles/r02_ab_attn_keysplit.txt): n = 197 (two key blocks) 113.5 us with 8 softmax
+  // warps + ping-pong against 113.0 us key-split; n = 577 (five blocks) 125.5 against 117.2 us.  Neither four warps per
+  // sub-partition nor de-phasing moves the n = 197 case: there the sub-partition alternates between TMEM -> register loads
+  // (S in fp32: 64 KB per sub-partition and item at 16 B/clk) and the exp / pack instruction stream, and both are needed in full.
+  // Key-split is used where it wins: more than two key blocks.  VB_ATTN_KEYSPLIT=0/1 forces a form.
+  static const char* ks_env = getenv("VB_ATTN_KEYSPLIT");
+  const bool key_split = ks_env != nullptr ? (ks_env[0] != '0') : (VB_ATTN_KEYSPLIT || nk > 2 * BKV);
+  if (first_use_on_this_device(seen)) {
+    VB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    VB_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+  }
   AttnKey key{q, ldq, k, ldk, v, ldv, out, ldo, B, nq, nk, heads};
   AttnPlan plan;                                   // copied out under the lock: another thread may clear the cache meanwhile
   {
@@ -527,7 +731,7 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   const float scale_log2 = (scale > 0.f ? scale : 1.0f / sqrtf(static_cast<float>(dh))) * 1.4426950408889634f;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(ATT_THREADS);
+  cfg.blockDim = dim3(key_split ? AttCfg<true>::THREADS : AttCfg<false>::THREADS);
   cfg.dynamicSmemBytes = ATT_SMEM;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -535,8 +739,10 @@ bool attention_fast<__nv_bfloat16>(const __nv_bfloat16* q, int ldq, const __nv_b
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel, plan.q, plan.k, plan.v, plan.o, heads, nq, nk,
-                             num_items, scale_log2, attn_trace_buffer()));
+  if (key_split) VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<true>, plan.q, plan.k, plan.v, plan.o, heads, nq, nk, num_items, scale_log2,
+                                            attn_trace_buffer()));
+  else VB_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<false>, plan.q, plan.k, plan.v, plan.o, heads, nq, nk, num_items, scale_log2,
+                                  attn_trace_buffer()));
   VB_CUDA(cudaGetLastError());
   count_launch();
   return true;
