@@ -17,6 +17,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SHAPES = {  # name: (N, K, bias, res, gelu) at M = 50432
     "qkv": (2304, 768, 0, 0, 0), "out_proj": (768, 768, 1, 1, 0), "fc1_gelu": (3072, 768, 1, 0, 1), "fc2": (768, 3072, 1, 1, 0),
+    "out_proj_cait": (384, 384, 1, 1, 0), "fc2_cait": (384, 1536, 1, 1, 0),          # these two at M = 25088 (CaiT-S36, B = 128)
 }   # plus ln_qkv / ln_fc1_gelu (LayerNorm-folded, as the model runs them), ln_*_cait (M = 25088, K = 384), attention, attention_l
 CHILD = r"""
 import sys, json, zlib
@@ -58,6 +59,7 @@ for name in ops:
         out[name] = dict(ms=ms, tflops=4.0 * B * h * n * n * 64 / ms / 1e9, crc=zlib.crc32(o.tobytes()))
     else:
         N, K, bias, res, gelu = shapes[name]
+        M = 25088 if name.endswith("cait") else 50432
         a = rng.standard_normal((M, K), dtype=np.float32)
         w = (rng.standard_normal((K, N), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
         b = rng.standard_normal(N).astype(np.float32) if bias else None
