@@ -48,7 +48,7 @@ def test_gemm_bf16_plain(lib, M, N, K):
 
 
 @pytest.mark.parametrize("bias,scale,res,gelu", [(1, 0, 0, 0), (1, 0, 0, 1), (1, 0, 1, 0), (1, 1, 1, 0), (0, 0, 1, 0), (1, 1, 1, 1)])
-@pytest.mark.parametrize("M,N,K", [(394, 768, 192), (5000, 384, 1536), (641, 2304, 768)])
+@pytest.mark.parametrize("M,N,K", [(394, 768, 192), (5000, 384, 1536), (641, 2304, 768), (700, 1152, 384)])   # last: 192-wide tiles
 def test_gemm_bf16_epilogues(lib, M, N, K, bias, scale, res, gelu):
     out, ref = _linear_case(lib, M, N, K, bias, scale, res, gelu, "bf16", seed=M + N)
     np.testing.assert_allclose(out, ref, rtol=BF16_RTOL, atol=BF16_ATOL)
@@ -230,7 +230,7 @@ def _ln_linear_ref(x, g, b, w, bias, gelu):
 
 @pytest.mark.parametrize("gelu", [False, True])
 @pytest.mark.parametrize("rows", ["normal", "offset50", "outliers"])
-@pytest.mark.parametrize("M,N,K", [(394, 768, 768), (1000, 3072, 1024), (130, 192, 384)])
+@pytest.mark.parametrize("M,N,K", [(394, 768, 768), (1000, 3072, 1024), (130, 192, 384), (515, 1152, 384)])
 def test_ln_folded_linear(lib, M, N, K, rows, gelu):
     """PreNorm + Dense as the bf16 engine runs it (vit.py:18-22 + :39/:59): LayerNorm folded into the GEMM, its (mean, rstd)
     reduced in the epilogue from one-pass fp32 (sum, sumsq) partials of the bf16 rows.  `offset50`: rows of mean 50 and
