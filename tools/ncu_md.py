@@ -12,7 +12,9 @@ KEYS = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "launch__
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "sm__warps_active.avg.pct_of_peak_sustained_active"]
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__m_xbar2l1tex_read_bytes.sum", "lts__cycles_elapsed.avg.per_second",
+        "lts__t_sectors_srcunit_tex_op_read.sum"]
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "Ghz": 1e9, "Mhz": 1e6, "hz": 1.0}
 
 
 def rows_of(path):
@@ -28,6 +30,12 @@ def raw(path):
         for k in KEYS:
             if k in hdr:
                 print(f"| {k} | {r[hdr.index(k)]} | {units[hdr.index(k)]} |")
+        try:   # derived: L2 -> SM delivery rate (the GEMMs' wall)
+            val = lambda k: float(r[hdr.index(k)]) * UNIT[units[hdr.index(k)]]
+            rate = val("l1tex__m_xbar2l1tex_read_bytes.sum") / val("gpu__time_duration.sum")
+            print(f"| derived: L2 -> L1 read rate | {rate / 1e12:.2f} TB/s = {rate / val('lts__cycles_elapsed.avg.per_second'):.0f} B per L2 clock | |")
+        except (ValueError, KeyError):
+            pass
         print()
 
 
