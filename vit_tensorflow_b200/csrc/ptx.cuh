@@ -38,11 +38,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Wait with a watchdog: a protocol bug traps (launch error surfaced to the host) instead of hanging the GPU.
+// VB_MBAR_LIGHT_SPIN=1 reads the watchdog clock only every 4096th failed try (3 instead of 8 instructions per try for a waiting
+// warp).  Measured neutral on the GEMMs and on the ViT-B/16 step and 2 % slower on the attention kernel
+// (profiles/r02_ab_mbar_spin.txt): each try_wait already suspends the warp for a hardware-defined interval, the spin is not what
+// the working warps compete with.  Off.
+#ifndef VB_MBAR_LIGHT_SPIN
+#define VB_MBAR_LIGHT_SPIN 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+#if VB_MBAR_LIGHT_SPIN
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfffu) == 0 && clock64() - t0 > 8000000000LL) {  // ~4 s at ~2 GHz
+#else
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 8000000000LL) {  // ~4 s at ~2 GHz
+#endif
       printf("vb: mbarrier watchdog: block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }
