@@ -33,6 +33,8 @@ __global__ void bench(float* out, long long* cycles) {
       if (KIND == 9) { unsigned r; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(a[i]), "f"(c)); a[i] = __uint_as_float(r); }   // F2FP
       if (KIND == 10) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i]));                                    // MUFU.RCP
       if (KIND == 11) asm volatile("add.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(d));                                  // FADD
+      if (KIND == 12) { unsigned r = __float_as_uint(a[i]); asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }   // bf16x2: ptxas emits TWO MUFU.EX2.BF16 (lo, .H1) + PRMT -- no packed SFU op on sm_100a
+      if (KIND == 13) { unsigned r = __float_as_uint(a[i]); asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(r)); a[i] = __uint_as_float(r); }        // MUFU.EX2 f16x2
     }
   }
   const long long t1 = clock64();
@@ -72,6 +74,8 @@ int main() {
   run<11>("FADD", dout, dcyc);
   run<6>("MUFU.EX2", dout, dcyc);
   run<10>("MUFU.RCP", dout, dcyc);
+  run<12>("MUFU.EX2 bf16x2 (2 results)", dout, dcyc);
+  run<13>("MUFU.EX2 f16x2 (2 results)", dout, dcyc);
   run<7>("FMNMX", dout, dcyc);
   run<9>("F2FP.BF16 pack", dout, dcyc);
   cudaError_t e = cudaGetLastError();
