@@ -188,6 +188,25 @@ struct vb_handle {
   std::vector<cudaEvent_t> event_pool;
   double prof_ms[PROF_NUM] = {0}, prof_flops[PROF_NUM] = {0}, prof_bytes[PROF_NUM] = {0};
   long long prof_calls[PROF_NUM] = {0};
+  // side streams of the per-image T2T soft-split attention (layer_t2t): forked from / joined into the forward's stream with
+  // timing-less events, so that the branch is part of a captured graph like everything else
+  static constexpr int T2T_MAX_STREAMS = 4;
+  cudaStream_t side_streams[T2T_MAX_STREAMS - 1] = {nullptr, nullptr, nullptr};
+  cudaEvent_t fork_event = nullptr, join_events[T2T_MAX_STREAMS - 1] = {nullptr, nullptr, nullptr};
+  void ensure_side_streams() {
+    if (fork_event != nullptr) return;
+    VB_CUDA(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+    for (int i = 0; i < T2T_MAX_STREAMS - 1; ++i) {
+      VB_CUDA(cudaStreamCreateWithFlags(&side_streams[i], cudaStreamNonBlocking));
+      VB_CUDA(cudaEventCreateWithFlags(&join_events[i], cudaEventDisableTiming));
+    }
+  }
+  void destroy_side_streams() {
+    if (fork_event == nullptr) return;
+    cudaEventDestroy(fork_event);
+    for (int i = 0; i < T2T_MAX_STREAMS - 1; ++i) { cudaEventDestroy(join_events[i]); cudaStreamDestroy(side_streams[i]); }
+    fork_event = nullptr;
+  }
   cudaEvent_t get_event() {
     if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
     cudaEvent_t e;
@@ -1185,8 +1204,24 @@ void vb_handle::layer_t2t<__nv_bfloat16>(__nv_bfloat16* X, int B, int n, const L
   bf* Y = arena.get<bf>(static_cast<size_t>(M) * Dp);
   bf* QKV = arena.get<bf>(static_cast<size_t>(M) * 3 * Dp);
   bf* Vt = arena.get<bf>(static_cast<size_t>(B) * Dp * npad);
-  float* S = arena.get<float>(static_cast<size_t>(n) * npad);
-  bf* P = arena.get<bf>(static_cast<size_t>(n) * npad);
+  // Images are independent: ns of them are in flight on ns streams (the forward's own + side streams), each with its own score /
+  // probability buffers.  The per-image kernels are small (16 pair tiles for Q K^T at n = 784) and strictly dependent, so one
+  // stream leaves most SMs idle and pays every launch gap (389 launches, 6.1 of the 6.9 ms T2T step at batch 64).  Two streams
+  // when one image's buffers are large (n = 3136: 59 MB, two of them still fit the 126 MB L2), four otherwise.
+  const size_t s_elems = static_cast<size_t>(n) * npad;
+  static const char* ns_env = getenv("VB_T2T_STREAMS");
+  int ns = ns_env != nullptr ? atoi(ns_env) : (s_elems * 6 > (48u << 20) ? 2 : 4);
+  ns = std::max(1, std::min(ns, std::min(B, static_cast<int>(T2T_MAX_STREAMS))));
+  if (profiling) ns = 1;                                         // per-class event timing wants one stream
+  float* S[T2T_MAX_STREAMS];
+  bf* P[T2T_MAX_STREAMS];
+  cudaStream_t st[T2T_MAX_STREAMS];
+  for (int i = 0; i < ns; ++i) { S[i] = arena.get<float>(s_elems); P[i] = arena.get<bf>(s_elems); }
+  st[0] = s;
+  if (ns > 1) {
+    ensure_side_streams();
+    for (int i = 1; i < ns; ++i) st[i] = side_streams[i - 1];
+  }
   { ProfScope ps(this, PROF_LN, 0.0, 4.0 * M * D, s); layernorm<bf>(X, Dp, l.attn_norm.gamma, l.attn_norm.beta, Y, Dp, M, D, s, Dp); }
   linear<bf>(Y, Dp, M, l.to_qkv, QKV, 3 * Dp, Epi(), s);
   {
@@ -1194,12 +1229,21 @@ void vb_handle::layer_t2t<__nv_bfloat16>(__nv_bfloat16* X, int B, int n, const L
     transpose_rows_bf16(QKV + 2 * Dp, 3 * Dp, static_cast<long long>(n) * 3 * Dp, Vt, npad, static_cast<long long>(Dp) * npad, B, n, npad, Dp, s);
   }
   const float scale_log2 = (1.0f / sqrtf(static_cast<float>(D))) * 1.4426950408889634f;
+  if (ns > 1) {
+    VB_CUDA(cudaEventRecord(fork_event, s));
+    for (int i = 1; i < ns; ++i) VB_CUDA(cudaStreamWaitEvent(st[i], fork_event, 0));
+  }
   for (int b = 0; b < B; ++b) {
+    const int i = b % ns;
     const bf* Qb = QKV + static_cast<size_t>(b) * n * 3 * Dp;
     bf* Xb = X + static_cast<size_t>(b) * n * Dp;
-    gemm_cached(Qb, 3 * Dp, Qb + Dp, 3 * Dp, n, S, npad, n, npad, Dp, nullptr, 0, true, PROF_ATTN, s);           // S = Q K^T
-    { ProfScope ps(this, PROF_ATTN, 0.0, 6.0 * n * npad, s); softmax_rows_bf16(S, npad, P, npad, n, n, npad, scale_log2, s); }
-    gemm_cached(P, npad, Vt + static_cast<size_t>(b) * Dp * npad, npad, 0, Xb, Dp, n, Dp, npad, Xb, Dp, false, PROF_ATTN, s);   // X += P V
+    gemm_cached(Qb, 3 * Dp, Qb + Dp, 3 * Dp, n, S[i], npad, n, npad, Dp, nullptr, 0, true, PROF_ATTN, st[i]);       // S = Q K^T
+    { ProfScope ps(this, PROF_ATTN, 0.0, 6.0 * n * npad, st[i]); softmax_rows_bf16(S[i], npad, P[i], npad, n, n, npad, scale_log2, st[i]); }
+    gemm_cached(P[i], npad, Vt + static_cast<size_t>(b) * Dp * npad, npad, 0, Xb, Dp, n, Dp, npad, Xb, Dp, false, PROF_ATTN, st[i]);   // X += P V
+  }
+  for (int i = 1; i < ns; ++i) {
+    VB_CUDA(cudaEventRecord(join_events[i - 1], st[i]));
+    VB_CUDA(cudaStreamWaitEvent(s, join_events[i - 1], 0));
   }
   { ProfScope ps(this, PROF_LN, 0.0, 4.0 * M * D, s); layernorm<bf>(X, Dp, l.ff_norm.gamma, l.ff_norm.beta, Y, Dp, M, D, s, Dp); }
   bf* Hb = arena.get<bf>(static_cast<size_t>(M) * Dp);
@@ -1726,6 +1770,7 @@ void vb_destroy(vb_handle* h) {
   for (auto& w : h->weights) if (w.dev) cudaFree(w.dev);
   h->prof_collect();
   for (auto e : h->event_pool) cudaEventDestroy(e);
+  h->destroy_side_streams();
   delete h;
 }
 
