@@ -23,6 +23,12 @@
 #include <tuple>
 #include <vector>
 
+#ifndef VB_FWD_STREAMS
+#define VB_FWD_STREAMS 1                 // 2 = split a large ViT batch into two half-batches on two streams (forward_impl); measured no gain
+#endif
+#ifndef VB_FWD_SPLIT_MIN_HALF
+#define VB_FWD_SPLIT_MIN_HALF 64         // smallest half-batch worth a stream of its own
+#endif
 namespace vb {
 namespace {
 
@@ -193,8 +199,13 @@ struct vb_handle {
   static constexpr int T2T_MAX_STREAMS = 4;
   cudaStream_t side_streams[T2T_MAX_STREAMS - 1] = {nullptr, nullptr, nullptr};
   cudaEvent_t fork_event = nullptr, join_events[T2T_MAX_STREAMS - 1] = {nullptr, nullptr, nullptr};
+  cudaStream_t half_stream = nullptr;                    // second half-batch of a split forward (forward_impl)
+  cudaEvent_t fwd_fork_event = nullptr, fwd_join_event = nullptr;
   void ensure_side_streams() {
     if (fork_event != nullptr) return;
+    VB_CUDA(cudaStreamCreateWithFlags(&half_stream, cudaStreamNonBlocking));
+    VB_CUDA(cudaEventCreateWithFlags(&fwd_fork_event, cudaEventDisableTiming));
+    VB_CUDA(cudaEventCreateWithFlags(&fwd_join_event, cudaEventDisableTiming));
     VB_CUDA(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
     for (int i = 0; i < T2T_MAX_STREAMS - 1; ++i) {
       VB_CUDA(cudaStreamCreateWithFlags(&side_streams[i], cudaStreamNonBlocking));
@@ -204,6 +215,7 @@ struct vb_handle {
   void destroy_side_streams() {
     if (fork_event == nullptr) return;
     cudaEventDestroy(fork_event);
+    cudaEventDestroy(fwd_fork_event); cudaEventDestroy(fwd_join_event); cudaStreamDestroy(half_stream);
     for (int i = 0; i < T2T_MAX_STREAMS - 1; ++i) { cudaEventDestroy(join_events[i]); cudaStreamDestroy(side_streams[i]); }
     fork_event = nullptr;
   }
@@ -969,10 +981,36 @@ struct vb_handle {
                                    accumulate ? logits : nullptr, hd.N, 0, s);
   }
 
+  // Images are independent, so a large batch can run as two half-batches on two streams (the forward's own and `half_stream`,
+  // forked / joined with timing-less events and therefore part of a captured graph): while one half's kernel drains -- last
+  // epilogues, CTAs finishing at different times, the dependent launch waiting for the whole grid -- the other half's next
+  // kernel already has CTAs on the freed SMs.  Results are bit-identical to the unsplit forward (every kernel's tile
+  // arithmetic is independent of the batch, tests: test_batch_independence_and_determinism).  Only for the kinds whose kernels
+  // keep no per-device scratch (the head-mixing attention kernel has one).
+  // MEASURED (profiles/r02_ab_fwd_streams.txt): correct (253 GPU tests, identical logits) but no faster -- ViT-B/16 B = 256
+  // 9.02 / 9.14 ms unsplit vs 9.42 / 9.11 ms split, ViT-L/16-384 47.06 vs 47.30 ms: every kernel here is a persistent grid of
+  // one CTA per SM, so the second stream's CTAs only get SMs as the first kernel's CTAs exit, and what the overlap of the tails
+  // gains the doubled per-launch cost (half the tiles per kernel) loses.  Off by default (VB_FWD_STREAMS=2 enables it).
   template <typename T>
   void forward_impl(const float* img, int B, int H, int Wd, float* logits, cudaStream_t s) {
-    const vb_config& c = cfg;
     arena.reset();
+    static const char* fs_env = getenv("VB_FWD_STREAMS");
+    const int want = fs_env != nullptr ? atoi(fs_env) : VB_FWD_STREAMS;
+    const bool split = want >= 2 && !profiling && bf16() && cfg.kind == VB_KIND_VIT && B >= 2 * VB_FWD_SPLIT_MIN_HALF;
+    if (!split) { forward_body<T>(img, B, H, Wd, logits, s); return; }
+    ensure_side_streams();
+    const int B0 = (B + 1) / 2;
+    VB_CUDA(cudaEventRecord(fwd_fork_event, s));
+    VB_CUDA(cudaStreamWaitEvent(half_stream, fwd_fork_event, 0));
+    forward_body<T>(img, B0, H, Wd, logits, s);
+    forward_body<T>(img + static_cast<size_t>(B0) * H * Wd * cfg.channels, B - B0, H, Wd, logits + static_cast<size_t>(B0) * cfg.num_classes, half_stream);
+    VB_CUDA(cudaEventRecord(fwd_join_event, half_stream));
+    VB_CUDA(cudaStreamWaitEvent(s, fwd_join_event, 0));
+  }
+
+  template <typename T>
+  void forward_body(const float* img, int B, int H, int Wd, float* logits, cudaStream_t s) {
+    const vb_config& c = cfg;
     if (c.kind == VB_KIND_VIT || c.kind == VB_KIND_DEEPVIT || c.kind == VB_KIND_T2T_VIT) {
       int rows = 0;
       float* stats = nullptr;
