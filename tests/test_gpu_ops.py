@@ -120,7 +120,8 @@ def _attention_ref(q, k, v, heads, variant, mix_a, mix_b, g, b):
 @pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("B,nq,nk,heads,dh", [(2, 197, 197, 3, 64), (3, 17, 17, 4, 16), (2, 1, 197, 4, 48), (1, 577, 577, 2, 64),
                                                (4, 65, 65, 2, 32), (2, 197, 197, 16, 64), (2, 196, 196, 8, 48),
-                                               (2, 1, 197, 8, 48), (1, 50, 50, 6, 32)])
+                                               (2, 1, 197, 8, 48), (1, 50, 50, 6, 32),
+                                               (3, 257, 257, 2, 64), (2, 258, 300, 1, 64)])   # last two: one / two query rows past a multiple of the item size
 def test_attention(lib, precision, variant, B, nq, nk, heads, dh):
     from vit_tensorflow_b200 import _lib
     rng = np.random.default_rng(nq * 7 + variant)

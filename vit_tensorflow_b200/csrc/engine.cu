@@ -1063,15 +1063,24 @@ struct vb_handle {
       T* lg_cls = arena.get<T>(static_cast<size_t>(B) * c.lg_dim);
       T* ctx_lg = arena.get<T>(static_cast<size_t>(B) * nl * c.lg_dim);   // [LN(Pin(sm_cls)) ; lg patches]
       T* ctx_sm = arena.get<T>(static_cast<size_t>(B) * ns * c.sm_dim);   // [LN(Pin(lg_cls)) ; sm patches]
+      // The two towers of a multi-scale block are independent until the cross-attention (cross_vit.py:185-190): the large-patch
+      // tower (n = 17 at the README configuration: GEMMs of a few tiles) runs on a side stream beside the small-patch one, forked
+      // and joined with timing-less events (part of the captured graph).  VB_CROSSVIT_STREAMS=1 keeps one stream.
+      static const char* xs_env = getenv("VB_CROSSVIT_STREAMS");
+      const bool two = (xs_env != nullptr ? atoi(xs_env) : 2) >= 2 && !profiling && bf16();
+      cudaStream_t sg = s;
+      if (two) { ensure_side_streams(); sg = side_streams[0]; }
       for (const auto& xb : xblocks) {
+        if (two) { VB_CUDA(cudaEventRecord(fork_event, s)); VB_CUDA(cudaStreamWaitEvent(sg, fork_event, 0)); }
         for (const auto& l : xb.sm_layers) layer_self<T>(S, B, ns, c.sm_dim, l, s, st_s, &sv_s);
         layernorm<T>(S, c.sm_dim, xb.sm_final.gamma, xb.sm_final.beta, S, c.sm_dim, B * ns, c.sm_dim, s);
-        for (const auto& l : xb.lg_layers) layer_self<T>(G, B, nl, c.lg_dim, l, s, st_g, &sv_g);
-        layernorm<T>(G, c.lg_dim, xb.lg_final.gamma, xb.lg_final.beta, G, c.lg_dim, B * nl, c.lg_dim, s);
+        for (const auto& l : xb.lg_layers) layer_self<T>(G, B, nl, c.lg_dim, l, sg, st_g, &sv_g);
+        layernorm<T>(G, c.lg_dim, xb.lg_final.gamma, xb.lg_final.beta, G, c.lg_dim, B * nl, c.lg_dim, sg);
         sv_s = sv_g = false;   // the trailing LayerNorm and the cls write-back below change the token rows
+        copy_tokens<T>(G, nl, 0, lg_cls, 1, 0, 1, B, c.lg_dim, sg);
+        copy_tokens<T>(G, nl, 1, ctx_lg, nl, 1, nl - 1, B, c.lg_dim, sg);
+        if (two) { VB_CUDA(cudaEventRecord(join_events[0], sg)); VB_CUDA(cudaStreamWaitEvent(s, join_events[0], 0)); }
         copy_tokens<T>(S, ns, 0, sm_cls, 1, 0, 1, B, c.sm_dim, s);
-        copy_tokens<T>(G, nl, 0, lg_cls, 1, 0, 1, B, c.lg_dim, s);
-        copy_tokens<T>(G, nl, 1, ctx_lg, nl, 1, nl - 1, B, c.lg_dim, s);
         copy_tokens<T>(S, ns, 1, ctx_sm, ns, 1, ns - 1, B, c.sm_dim, s);
         for (size_t R = 0; R < xb.sm_attend_lg.size(); ++R) {
           cross_attend<T>(sm_cls, c.sm_dim, ctx_lg, nl, c.lg_dim, xb.sm_attend_lg[R], B, s);
