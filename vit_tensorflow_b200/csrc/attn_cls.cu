@@ -5,7 +5,7 @@
 // With one query row per image there is nothing for a tensor core to do (M = 1): the op is a read of K and V
 // (B * nk * 2 * heads * dh bf16 values, 38.7 MB at the CaiT-S36 cls stage, B = 128) plus O(heads^2 nk) arithmetic per image.
 // One CTA per image, everything between the loads in shared memory:
-//   1. scores   S[h][j] = scale * q_h . k_{j,h}        thread = key j, 16-byte loads along its K row, q broadcast from smem
+//   1. scores   S[h][j] = scale * q_h . k_{j,h}        thread = (key j, head h), 16-byte loads along the head's slice of the K row
 //   2. variant 2: S <- mix_pre^T S (cait.py:123)        thread = key j
 //   3. softmax over j per head                          warp = head (shuffle reductions, exp2 on pre-scaled scores)
 //   4. variant 2: P <- mix_post^T P (cait.py:125); variant 1: P <- LN_heads(W^T P) (deepvit.py:83-84)     thread = key j
@@ -46,21 +46,31 @@ attn_cls_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat1
   }
   __syncthreads();
   // ---- 1. scores (in log2 units: scale * log2(e) folded in; the pre-softmax mix is linear, so it commutes with the factor)
+  // thread = (key j, head h), adjacent threads = adjacent heads of one key: a warp's eight 16-byte loads per thread sweep four
+  // whole K rows (4 KB, L1-resident), all issued before the arithmetic.  (The first form -- thread = key, 64 dependent loads
+  // along a 1 KB row, 32 KB of rows per warp -- ran CrossViT's 257-key cross-attention at ~220 us per launch.)
   const int chunks = dh >> 3;
-  for (int j = tid; j < nk; j += CLS_THREADS) {
-    const uint4* kr = reinterpret_cast<const uint4*>(k + (static_cast<size_t>(b) * nk + j) * ldk);
-    for (int h = 0; h < heads; ++h) {
-      float acc = 0.f;
-      for (int c = 0; c < chunks; ++c) {
-        const uint4 w = __ldg(kr + h * chunks + c);
-        const float* qq = sq + h * dh + c * 8;
-        acc = fmaf(bf16_lo(w.x), qq[0], acc); acc = fmaf(bf16_hi(w.x), qq[1], acc);
-        acc = fmaf(bf16_lo(w.y), qq[2], acc); acc = fmaf(bf16_hi(w.y), qq[3], acc);
-        acc = fmaf(bf16_lo(w.z), qq[4], acc); acc = fmaf(bf16_hi(w.z), qq[5], acc);
-        acc = fmaf(bf16_lo(w.w), qq[6], acc); acc = fmaf(bf16_hi(w.w), qq[7], acc);
+  for (int idx = tid; idx < nk * heads; idx += CLS_THREADS) {
+    const int j = idx / heads, h = idx - j * heads;
+    const uint4* kr = reinterpret_cast<const uint4*>(k + (static_cast<size_t>(b) * nk + j) * ldk) + h * chunks;
+    const float* qh = sq + h * dh;
+    float acc = 0.f;
+    for (int c0 = 0; c0 < chunks; c0 += 8) {
+      uint4 w[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) w[c] = (c0 + c < chunks) ? __ldg(kr + c0 + c) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c0 + c < chunks) {
+          const float* qq = qh + (c0 + c) * 8;
+          acc = fmaf(bf16_lo(w[c].x), qq[0], acc); acc = fmaf(bf16_hi(w[c].x), qq[1], acc);
+          acc = fmaf(bf16_lo(w[c].y), qq[2], acc); acc = fmaf(bf16_hi(w[c].y), qq[3], acc);
+          acc = fmaf(bf16_lo(w[c].z), qq[4], acc); acc = fmaf(bf16_hi(w[c].z), qq[5], acc);
+          acc = fmaf(bf16_lo(w[c].w), qq[6], acc); acc = fmaf(bf16_hi(w[c].w), qq[7], acc);
+        }
       }
-      sA[h * nk + j] = acc * scale_log2;
     }
+    sA[h * nk + j] = acc * scale_log2;
   }
   __syncthreads();
   float* cur = sA;
@@ -117,17 +127,23 @@ attn_cls_kernel(const __nv_bfloat16* __restrict__ q, int ldq, const __nv_bfloat1
     const int e = e2 * 2, h = e / dh;
     const float* p = cur + h * nk;
     const __nv_bfloat16* vc = v + static_cast<size_t>(b) * nk * ldv + e;
+    // eight independent row loads in flight per thread (the two-deep form was latency-bound: nk / 2 dependent L2 round trips)
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
     int j = 0;
-    for (; j + 1 < nk; j += 2) {
-      const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(j) * ldv));
-      const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(j + 1) * ldv));
-      a0 = fmaf(p[j], bf16_lo(w0), a0); a1 = fmaf(p[j], bf16_hi(w0), a1);
-      c0 = fmaf(p[j + 1], bf16_lo(w1), c0); c1 = fmaf(p[j + 1], bf16_hi(w1), c1);
+    for (; j + 7 < nk; j += 8) {
+      uint32_t w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldg(reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(j + u) * ldv));
+#pragma unroll
+      for (int u = 0; u < 8; u += 2) {
+        a0 = fmaf(p[j + u], bf16_lo(w[u]), a0); a1 = fmaf(p[j + u], bf16_hi(w[u]), a1);
+        c0 = fmaf(p[j + u + 1], bf16_lo(w[u + 1]), c0); c1 = fmaf(p[j + u + 1], bf16_hi(w[u + 1]), c1);
+      }
     }
-    if (j < nk) {
+    for (; j < nk; ++j) {                                          // even keys -> (a0, a1), odd keys -> (c0, c1), as in the main loop
       const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(vc + static_cast<size_t>(j) * ldv));
-      a0 = fmaf(p[j], bf16_lo(w0), a0); a1 = fmaf(p[j], bf16_hi(w0), a1);
+      if (j & 1) { c0 = fmaf(p[j], bf16_lo(w0), c0); c1 = fmaf(p[j], bf16_hi(w0), c1); }
+      else { a0 = fmaf(p[j], bf16_lo(w0), a0); a1 = fmaf(p[j], bf16_hi(w0), a1); }
     }
     *reinterpret_cast<uint32_t*>(out + static_cast<size_t>(b) * ldo + e) = pack_bf16x2(a0 + c0, a1 + c1);
   }
