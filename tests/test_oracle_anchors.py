@@ -8,6 +8,8 @@ implementations of the same published operators, on random inputs.  None of this
   LayerNormalization eps 1e-3 (vit.py:18)   F.layer_norm
   exact-erf GELU (vit.py:29-34)             F.gelu(approximate='none')
   Rearrange patches (vit.py:142)            F.unfold with kernel = stride = patch (window order) -- besides einops itself
+  talking heads / re-attention (cait.py:114-127, deepvit.py:79-87)   plain-loop restatements without einsum / einops: which axis of the
+                                            [h, g] mix matrices is contracted, LayerNorm over the head axis, head-major column order
 """
 import numpy as np
 import pytest
@@ -81,3 +83,77 @@ def test_layernorm_and_gelu_vs_torch():
     ref = F.layer_norm(torch.from_numpy(x), (48,), torch.from_numpy(w["n.gamma"]), torch.from_numpy(w["n.beta"]), eps=1e-3).numpy()
     np.testing.assert_allclose(S.layer_norm(x, w, "n"), ref, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(S.gelu(x), F.gelu(torch.from_numpy(x), approximate="none").numpy(), rtol=1e-12, atol=1e-14)
+
+
+def _explicit_head_mix(t, W):
+    """out[b, g, i, j] = sum_h t[b, h, i, j] * W[h, g] written as plain loops: the meaning TensorFlow documents for
+    einsum('b h i j, h g -> b g i j') (deepvit.py:83, cait.py:123,125)."""
+    b, h, n, m = t.shape
+    out = np.zeros((b, W.shape[1], n, m))
+    for bb in range(b):
+        for g in range(W.shape[1]):
+            for hh in range(h):
+                out[bb, g] += t[bb, hh] * W[hh, g]
+    return out
+
+
+def test_cait_talking_heads_vs_explicit_loops():
+    """cait.py:114-127 restated without einsum / einops: projections, per-head scores, pre-softmax mix over the IN-head axis,
+    softmax over keys, post-softmax mix, P V, heads merged head-major."""
+    rng = np.random.default_rng(5)
+    b, h, n, d, dim = 2, 3, 7, 4, 10
+    x = rng.standard_normal((b, n, dim))
+    w = {"l.to_q.kernel": rng.standard_normal((dim, h * d)), "l.to_kv.kernel": rng.standard_normal((dim, 2 * h * d)),
+         "l.mix_pre": rng.standard_normal((h, h)), "l.mix_post": rng.standard_normal((h, h)),
+         "l.to_out.kernel": rng.standard_normal((h * d, dim)), "l.to_out.bias": rng.standard_normal(dim)}
+    got = S.attention_qkv(x, w, "l.", h, d, talking_heads=True)
+    q = x @ w["l.to_q.kernel"]
+    kv = x @ w["l.to_kv.kernel"]
+    k, v = kv[..., :h * d], kv[..., h * d:]                                    # tf.split(kv, 2): [k | v]
+    dots = np.zeros((b, h, n, n))
+    for hh in range(h):                                                        # 'b n (h d) -> b h n d': column = h * d + d'
+        qs, ks = q[..., hh * d:(hh + 1) * d], k[..., hh * d:(hh + 1) * d]
+        for bb in range(b):
+            dots[bb, hh] = qs[bb] @ ks[bb].T * d ** -0.5
+    dots = _explicit_head_mix(dots, w["l.mix_pre"])
+    e = np.exp(dots - dots.max(-1, keepdims=True))
+    attn = _explicit_head_mix(e / e.sum(-1, keepdims=True), w["l.mix_post"])
+    out = np.zeros((b, n, h * d))
+    for hh in range(h):
+        for bb in range(b):
+            out[bb, :, hh * d:(hh + 1) * d] = attn[bb, hh] @ v[bb, :, hh * d:(hh + 1) * d]
+    ref = out @ w["l.to_out.kernel"] + w["l.to_out.bias"]
+    np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+def test_deepvit_reattention_vs_explicit_loops():
+    """deepvit.py:79-87 restated with loops: softmax, head mix, LayerNorm over the HEAD axis of every (query, key) pair
+    (eps 1e-3, biased variance, gamma / beta indexed by head), then P V."""
+    rng = np.random.default_rng(6)
+    b, h, n, d = 2, 4, 6, 3
+    dim = h * d
+    x = rng.standard_normal((b, n, dim))
+    w = {"l.to_qkv.kernel": rng.standard_normal((dim, 3 * dim)), "l.reattn_weights": rng.standard_normal((h, h)),
+         "l.reattn_norm.gamma": rng.uniform(0.5, 1.5, h), "l.reattn_norm.beta": rng.standard_normal(h)}
+    got = S.attention_vit(x, w, "l.", h, d, deepvit=True)
+    qkv = x @ w["l.to_qkv.kernel"]
+    q, k, v = qkv[..., :dim], qkv[..., dim:2 * dim], qkv[..., 2 * dim:]
+    attn = np.zeros((b, h, n, n))
+    for bb in range(b):
+        for hh in range(h):
+            s = q[bb, :, hh * d:(hh + 1) * d] @ k[bb, :, hh * d:(hh + 1) * d].T * d ** -0.5
+            e = np.exp(s - s.max(-1, keepdims=True))
+            attn[bb, hh] = e / e.sum(-1, keepdims=True)
+    mixed = _explicit_head_mix(attn, w["l.reattn_weights"])
+    normed = np.zeros_like(mixed)
+    for bb in range(b):
+        for i in range(n):
+            for j in range(n):
+                col = mixed[bb, :, i, j]
+                mu, var = col.mean(), ((col - col.mean()) ** 2).mean()
+                normed[bb, :, i, j] = (col - mu) / np.sqrt(var + 1e-3) * w["l.reattn_norm.gamma"] + w["l.reattn_norm.beta"]
+    ref = np.zeros((b, n, dim))
+    for bb in range(b):
+        for hh in range(h):
+            ref[bb, :, hh * d:(hh + 1) * d] = normed[bb, hh] @ v[bb, :, hh * d:(hh + 1) * d]
+    np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10)
