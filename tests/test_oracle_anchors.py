@@ -157,3 +157,54 @@ def test_deepvit_reattention_vs_explicit_loops():
         for hh in range(h):
             ref[bb, :, hh * d:(hh + 1) * d] = normed[bb, hh] @ v[bb, :, hh * d:(hh + 1) * d]
     np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+def test_crossvit_cross_attention_vs_explicit_loops():
+    """cross_vit.py:128-138 + 69-93 + 159-160 restated with loops: project_in -> LayerNorm of the query token only -> keys /
+    values over [normed query ; raw context] (kv_include_self) -> per-head softmax attention -> to_out -> project_out -> + cls."""
+    rng = np.random.default_rng(7)
+    b, m, d_q, d_c, h, dh = 2, 5, 6, 10, 2, 4                                  # query branch width 6, context branch width 10
+    cls, ctx = rng.standard_normal((b, 1, d_q)), rng.standard_normal((b, m, d_c))
+    cfg = dict(cross_attn_heads=h, cross_attn_dim_head=dh)
+    w = {"x.project_in.kernel": rng.standard_normal((d_q, d_c)), "x.project_in.bias": rng.standard_normal(d_c),
+         "x.project_out.kernel": rng.standard_normal((d_c, d_q)), "x.project_out.bias": rng.standard_normal(d_q),
+         "x.norm.gamma": rng.uniform(0.5, 1.5, d_c), "x.norm.beta": rng.standard_normal(d_c),
+         "x.to_q.kernel": rng.standard_normal((d_c, h * dh)), "x.to_kv.kernel": rng.standard_normal((d_c, 2 * h * dh)),
+         "x.to_out.kernel": rng.standard_normal((h * dh, d_c)), "x.to_out.bias": rng.standard_normal(d_c)}
+    got = S._cross_attend(cls, ctx, w, cfg, "x.")
+    ref = np.zeros_like(cls)
+    for bb in range(b):
+        x = cls[bb, 0] @ w["x.project_in.kernel"] + w["x.project_in.bias"]
+        xn = (x - x.mean()) / np.sqrt(((x - x.mean()) ** 2).mean() + 1e-3) * w["x.norm.gamma"] + w["x.norm.beta"]
+        rows = np.vstack([xn[None, :], ctx[bb]])                               # the normed query token is key / value row 0
+        q = xn @ w["x.to_q.kernel"]
+        kv = rows @ w["x.to_kv.kernel"]
+        k, v = kv[:, :h * dh], kv[:, h * dh:]
+        o = np.zeros(h * dh)
+        for hh in range(h):
+            s = k[:, hh * dh:(hh + 1) * dh] @ q[hh * dh:(hh + 1) * dh] * dh ** -0.5
+            p = np.exp(s - s.max())
+            o[hh * dh:(hh + 1) * dh] = (p / p.sum()) @ v[:, hh * dh:(hh + 1) * dh]
+        y = o @ w["x.to_out.kernel"] + w["x.to_out.bias"]
+        ref[bb, 0] = y @ w["x.project_out.kernel"] + w["x.project_out.bias"] + cls[bb, 0]
+    np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+def test_patch_merger_vs_explicit_loops():
+    """vit_with_patch_merger.py:49-55 with loops: LayerNorm, similarity of every learned query with every (scaled) token, softmax
+    over the TOKENS, weighted sum of the normed tokens."""
+    rng = np.random.default_rng(8)
+    b, n, d, t = 2, 9, 6, 3
+    x = rng.standard_normal((b, n, d))
+    w = {"patch_merger.norm.gamma": rng.uniform(0.5, 1.5, d), "patch_merger.norm.beta": rng.standard_normal(d),
+         "patch_merger.queries": rng.standard_normal((t, d))}
+    got = S.patch_merger(x, w)
+    ref = np.zeros((b, t, d))
+    for bb in range(b):
+        xn = np.stack([(r - r.mean()) / np.sqrt(((r - r.mean()) ** 2).mean() + 1e-3) * w["patch_merger.norm.gamma"]
+                       + w["patch_merger.norm.beta"] for r in x[bb]])
+        for tt in range(t):
+            s = np.array([w["patch_merger.queries"][tt] @ (xn[i] * d ** -0.5) for i in range(n)])
+            p = np.exp(s - s.max())
+            ref[bb, tt] = (p / p.sum()) @ xn
+    np.testing.assert_allclose(got, ref, rtol=1e-10, atol=1e-10)
