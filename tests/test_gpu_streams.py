@@ -52,6 +52,8 @@ def _digest(case, batch, env):
     ("t2t_mid", 6, "VB_T2T_STREAMS", ("1", "2", "4")),              # n = 3136 and n = 784 soft-split layers on the tensor-core path
     ("crossvit_small", 5, "VB_CROSSVIT_STREAMS", ("1", "2")),
     ("vit_b128", 130, "VB_FWD_STREAMS", ("1", "2")),                 # 2 x 65 images: above the half-batch threshold of the split
+    ("cait_small", 130, "VB_FWD_STREAMS", ("1", "2")),               # head-mixing attention: one scratch per stream
+    ("deepvit_small", 130, "VB_FWD_STREAMS", ("1", "2")),
 ])
 def test_stream_count_does_not_change_the_bits(lib, case, batch, var, values):
     digests = {v: _digest(case, batch, {var: v}) for v in values}

@@ -34,6 +34,8 @@
 // written and read back by the same CTA within microseconds and overwritten by its next item: it lives in the 126 MB L2, not
 // in HBM -- the "score tensor" of the reference (2 x B h n^2 fp32 through memory) never exists.
 // Algorithmic bytes per launch: 2 B (nq + 2 nk) h dh + 2 B nq h dh (q, k, v in; out).
+#include <map>
+#include <utility>
 #include "attention.cuh"
 #include "kernels.cuh"
 #include "ptx.cuh"
@@ -467,12 +469,13 @@ attn_mix_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-// per-device scratch for the mixed attention weights (grows, never shrinks; allocated outside any stream capture: the first
-// call of a shape is always eager)
+// scratch for the mixed attention weights, one per (device, stream): kernels on different streams of one device (two handles
+// driven by two threads, the two half-batches of a split forward) may run concurrently and each CTA owns slot blockIdx.x of ITS
+// launch's scratch.  Grows, never shrinks; allocated outside any stream capture (the first call of a shape is always eager).
 struct MixScratch { void* p = nullptr; size_t bytes = 0; };
-MixScratch& mix_scratch(int dev) {
-  static MixScratch s[64];
-  return s[dev & 63];
+MixScratch& mix_scratch(int dev, cudaStream_t s) {
+  static std::map<std::pair<int, cudaStream_t>, MixScratch> m;
+  return m[std::make_pair(dev, s)];
 }
 
 template <int H, int VARIANT, bool SPLIT>
@@ -496,7 +499,7 @@ void launch_mix(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap&
   void* scratch = nullptr;
   {
     std::lock_guard<std::mutex> lock(global_cache_mutex());
-    MixScratch& ms = mix_scratch(dev);
+    MixScratch& ms = mix_scratch(dev, s);
     const size_t need = static_cast<size_t>(nsm) * slot_bytes;
     if (need > ms.bytes) {
       if (ms.p) { cudaDeviceSynchronize(); cudaFree(ms.p); ms.p = nullptr; ms.bytes = 0; }

@@ -985,8 +985,8 @@ struct vb_handle {
   // forked / joined with timing-less events and therefore part of a captured graph): while one half's kernel drains -- last
   // epilogues, CTAs finishing at different times, the dependent launch waiting for the whole grid -- the other half's next
   // kernel already has CTAs on the freed SMs.  Results are bit-identical to the unsplit forward (every kernel's tile
-  // arithmetic is independent of the batch, tests: test_batch_independence_and_determinism).  Only for the kinds whose kernels
-  // keep no per-device scratch (the head-mixing attention kernel has one).
+  // arithmetic is independent of the batch, tests: test_batch_independence_and_determinism).  ViT, DeepViT and CaiT only (the
+  // head-mixing attention kernel's scratch is per stream; T2T and CrossViT fork streams of their own).
   // MEASURED (profiles/r02_ab_fwd_streams.txt): correct (253 GPU tests, identical logits) but no faster -- ViT-B/16 B = 256
   // 9.02 / 9.14 ms unsplit vs 9.42 / 9.11 ms split, ViT-L/16-384 47.06 vs 47.30 ms: every kernel here is a persistent grid of
   // one CTA per SM, so the second stream's CTAs only get SMs as the first kernel's CTAs exit, and what the overlap of the tails
@@ -996,7 +996,8 @@ struct vb_handle {
     arena.reset();
     static const char* fs_env = getenv("VB_FWD_STREAMS");
     const int want = fs_env != nullptr ? atoi(fs_env) : VB_FWD_STREAMS;
-    const bool split = want >= 2 && !profiling && bf16() && cfg.kind == VB_KIND_VIT && B >= 2 * VB_FWD_SPLIT_MIN_HALF;
+    const bool split = want >= 2 && !profiling && bf16() && B >= 2 * VB_FWD_SPLIT_MIN_HALF &&
+                       (cfg.kind == VB_KIND_VIT || cfg.kind == VB_KIND_DEEPVIT || cfg.kind == VB_KIND_CAIT);
     if (!split) { forward_body<T>(img, B, H, Wd, logits, s); return; }
     ensure_side_streams();
     const int B0 = (B + 1) / 2;
