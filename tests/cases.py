@@ -52,6 +52,18 @@ MID = {
                      mlp_dim=384, dim_head=48),
 }
 
+# BASELINE.json configs[1..4] (batch replaced by 2: the path has no cross-image op, see test_batch_independence)
+FULL = {
+    "c2_vit_b16_224": dict(kind="vit", image_size=224, patch_size=16, num_classes=1000, dim=768, depth=12, heads=12, mlp_dim=3072),
+    "c3_deepvit_1024x24": dict(kind="deepvit", image_size=224, patch_size=16, num_classes=1000, dim=1024, depth=24, heads=16,
+                               mlp_dim=4096),
+    "c4_cait_s36_dh48": dict(kind="cait", image_size=224, patch_size=16, num_classes=1000, dim=384, depth=36, cls_depth=2, heads=8,
+                             mlp_dim=1536, dim_head=48),
+    "c4_cait_s36_dh64": dict(kind="cait", image_size=224, patch_size=16, num_classes=1000, dim=384, depth=36, cls_depth=2, heads=8,
+                             mlp_dim=1536, dim_head=64),
+    "c5_vit_l16_384": dict(kind="vit", image_size=384, patch_size=16, num_classes=1000, dim=1024, depth=24, heads=16, mlp_dim=4096),
+}
+
 
 def cfg_of(name):
     d = dict({**SMALL, **MID}[name])

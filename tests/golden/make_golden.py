@@ -2,9 +2,10 @@
 
     PYTHONPATH=. python tests/golden/make_golden.py
 
-The reference itself cannot run in this image (no TensorFlow) so these vectors pin the
-ORACLE ("parity unpinned" at the TF boundary).  `tools/ref_tf_dump.py` regenerates them from the real reference
-wherever TensorFlow is available; the two must agree to fp32 round-off.
+These vectors pin the ORACLE's own output (so that later edits cannot drift).  The vectors produced by the reference's
+own code are the `*__refshim.npz` files next to them (tests/golden/make_ref_golden.py: unmodified reference modules over
+the numpy TensorFlow stand-in of oracle/tf_shim.py); `tools/ref_tf_dump.py` regenerates them with real TensorFlow
+wherever it is available; all three must agree to fp32 round-off.
 Fixtures hold config + seeds + float64 logits only (weights/images are regenerated from the seeds)."""
 import json
 import os

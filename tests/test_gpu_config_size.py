@@ -15,20 +15,9 @@ import pytest
 
 import oracle
 from oracle import ref_torch
+from cases import FULL  # BASELINE.json configs[1..4] at batch 2
 
 pytestmark = pytest.mark.gpu
-
-# BASELINE.json configs[1..4] (batch replaced by 2: the path has no cross-image op, see test_batch_independence)
-FULL = {
-    "c2_vit_b16_224": dict(kind="vit", image_size=224, patch_size=16, num_classes=1000, dim=768, depth=12, heads=12, mlp_dim=3072),
-    "c3_deepvit_1024x24": dict(kind="deepvit", image_size=224, patch_size=16, num_classes=1000, dim=1024, depth=24, heads=16,
-                               mlp_dim=4096),
-    "c4_cait_s36_dh48": dict(kind="cait", image_size=224, patch_size=16, num_classes=1000, dim=384, depth=36, cls_depth=2, heads=8,
-                             mlp_dim=1536, dim_head=48),
-    "c4_cait_s36_dh64": dict(kind="cait", image_size=224, patch_size=16, num_classes=1000, dim=384, depth=36, cls_depth=2, heads=8,
-                             mlp_dim=1536, dim_head=64),
-    "c5_vit_l16_384": dict(kind="vit", image_size=384, patch_size=16, num_classes=1000, dim=1024, depth=24, heads=16, mlp_dim=4096),
-}
 
 # |err| <= ATOL + RTOL * |ref| on logits of standard deviation ~1 (|ref| max 2.6 - 4.3).  Measured maxima on the B200 are in
 # the comment of each line; the bound is <= 3x that.
@@ -77,3 +66,8 @@ def test_bf16_vs_oracle_at_config_size(lib, name, gen):
     print(f"\n[config-size parity] {name} {gen}: " + ", ".join(f"{k}={v:.4g}" for k, v in rec.items()))
     _record(name, gen, rec)
     assert (err <= atol + rtol * np.abs(ref)).all(), f"max err {err.max():.4f}, worst ratio {rec['worst_ratio']:.2f}"
+    # the same bound against what the REFERENCE'S OWN CODE computed for this configuration (unmodified vit_tensorflow classes
+    # over the numpy TensorFlow stand-in, float32; tests/golden/make_ref_golden.py) -- the oracle above agrees with it to 6e-6
+    zr = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}__{gen}__refshim.npz"))["logits_ref_f32"].astype(np.float64)
+    assert np.abs(zr - ref).max() < 5e-5
+    assert (np.abs(got - zr) <= atol + rtol * np.abs(zr)).all(), f"vs reference-code logits: max err {np.abs(got - zr).max():.4f}"

@@ -40,6 +40,10 @@ def test_fp32_gate_vs_oracle(lib, name, gen):
     # committed golden fixture of the same case
     z = np.load(os.path.join(GOLDEN, f"{name}__{gen}.npz"))
     np.testing.assert_allclose(got, z["logits_f64"], rtol=1e-3, atol=1e-4)
+    # ... and the logits the REFERENCE'S OWN CODE gave for it (unmodified vit_tensorflow modules over the numpy TensorFlow
+    # stand-in, tests/golden/make_ref_golden.py): the CUDA path against the reference, not against our restatement
+    zr = np.load(os.path.join(GOLDEN, f"{name}__{gen}__refshim.npz"))
+    np.testing.assert_allclose(got, zr["logits_ref_f64"], rtol=1e-3, atol=1e-4)
 
 
 @pytest.mark.parametrize("name", sorted(SMALL) + sorted(MID))

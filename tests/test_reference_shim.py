@@ -1,0 +1,277 @@
+"""The oracle pinned on the REFERENCE'S OWN CODE.
+
+TensorFlow is not installable here, but the reference is pure Python over `tensorflow` + `einops`: oracle/tf_shim.py puts a
+numpy implementation of the ~35 TensorFlow / Keras entry points it calls into sys.modules, and the unmodified modules of
+/root/reference/vit_tensorflow then run as written.  Three layers of checks:
+
+1. the stand-in's primitives against PyTorch's independent operators (Dense / LayerNormalization eps 1e-3 / softmax / exact
+   GELU / extract_patches SAME / Keras `training` plumbing) -- what remains ASSUMED about TensorFlow is exactly this list;
+2. LIVE (skipped where /root/reference is absent, i.e. on the GPU box): every model class of SURVEY.md section 8 (a) and (f),
+   constructed by the reference's own `__init__`, weights loaded by Keras attribute path, `model(img, training=False)` ==
+   oracle.forward_numpy to 1e-12 in float64;
+3. the committed fixtures tests/golden/*__refshim.npz (the same outputs, stored so that they travel) == the oracle, for the
+   small cases and for every BASELINE.json configuration at its own size.  The GPU tests compare the CUDA engine with these.
+"""
+import glob
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from oracle import ref_bind, ref_torch, spec_numpy, tf_shim
+from cases import FULL, SMALL
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+REF_DIR = "/root/reference/vit_tensorflow"
+live = pytest.mark.skipif(not os.path.isdir(REF_DIR), reason="reference checkout not present (GPU box): fixtures cover it")
+
+
+@pytest.fixture
+def f64():
+    tf_shim.set_dtype(np.float64)
+    yield
+    tf_shim.set_dtype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------ 1. primitives vs torch
+def test_shim_dense_layernorm_softmax_gelu_against_torch(f64):
+    rng = np.random.default_rng(0)
+    with tf_shim.installed() as tf:
+        import tensorflow.keras.layers as nn
+        x = rng.standard_normal((3, 7, 10))
+        d = nn.Dense(units=6)
+        d(x)                                                               # builds kernel [10, 6] + bias [6]
+        k, b = rng.standard_normal((10, 6)), rng.standard_normal(6)
+        d.set_weights([k, b])
+        np.testing.assert_allclose(d(x), F.linear(torch.from_numpy(x), torch.from_numpy(k).T, torch.from_numpy(b)).numpy(), atol=1e-12)
+        assert d.kernel.shape == (10, 6) and nn.Dense(units=4, use_bias=False)(x).shape == (3, 7, 4)
+        ln = nn.LayerNormalization()
+        ln(x)
+        g, be = 1 + 0.3 * rng.standard_normal(10), rng.standard_normal(10)
+        ln.set_weights([g, be])
+        ref = F.layer_norm(torch.from_numpy(x), (10,), torch.from_numpy(g), torch.from_numpy(be), eps=1e-3).numpy()
+        np.testing.assert_allclose(ln(x), ref, atol=1e-12)                 # Keras default epsilon = 1e-3 (NOT torch's 1e-5)
+        assert np.abs(ln(x) - F.layer_norm(torch.from_numpy(x), (10,), torch.from_numpy(g), torch.from_numpy(be)).numpy()).max() > 1e-5
+        np.testing.assert_allclose(nn.Softmax()(x), torch.softmax(torch.from_numpy(x), -1).numpy(), atol=1e-14)
+        np.testing.assert_allclose(tf.nn.softmax(x, axis=-1), nn.Softmax()(x), atol=0)
+        gelu = 0.5 * x * (1.0 + tf.math.erf(x / tf.cast(1.4142135623730951, x.dtype)))     # the reference's expression, vit.py:35
+        np.testing.assert_allclose(gelu, F.gelu(torch.from_numpy(x)).numpy(), atol=1e-14)
+        # tf.einsum ignores blanks; tf.matmul broadcasts batch dimensions (vit_with_patch_merger.py:51); tf.split in equal parts
+        q = rng.standard_normal((2, 3, 5, 4))
+        np.testing.assert_allclose(tf.einsum('b h i d, b h j d -> b h i j', q, q), torch.einsum('bhid,bhjd->bhij', torch.from_numpy(q), torch.from_numpy(q)).numpy(), atol=1e-12)
+        m = tf.matmul(rng.standard_normal((4, 10)), tf.transpose(x, perm=[0, 2, 1]))
+        assert m.shape == (3, 4, 7)
+        a, b2, c = tf.split(x[..., :9], num_or_size_splits=3, axis=-1)
+        assert a.shape == (3, 7, 3) and np.array_equal(np.concatenate([a, b2, c], -1), x[..., :9])
+
+
+@pytest.mark.parametrize("H,W,k,s", [(32, 32, 7, 4), (8, 8, 3, 2), (9, 13, 3, 2), (7, 7, 3, 2), (16, 16, 3, 1), (5, 6, 7, 4)])
+def test_shim_extract_patches_same_against_torch_unfold(f64, H, W, k, s):
+    """tf.image.extract_patches(padding='SAME') (t2t.py:43) against F.unfold on an explicitly padded image: total padding
+    max((ceil(in/s)-1)*s + k - in, 0), smaller half first; patch vector (row, col, channel)."""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, H, W, 3))
+    with tf_shim.installed() as tf:
+        got = tf.image.extract_patches(x, sizes=[1, k, k, 1], strides=[1, s, s, 1], rates=[1, 1, 1, 1], padding='SAME')
+    oh, ow = -(-H // s), -(-W // s)
+    th, tw = max((oh - 1) * s + k - H, 0), max((ow - 1) * s + k - W, 0)
+    xt = F.pad(torch.from_numpy(x).permute(0, 3, 1, 2), (tw // 2, tw - tw // 2, th // 2, th - th // 2))
+    u = F.unfold(xt, kernel_size=k, stride=s)                               # [b, C*k*k, L], channel slowest
+    u = u.reshape(2, 3, k, k, -1)[..., :].permute(0, 4, 2, 3, 1)            # [b, L', k, k, C]
+    # unfold may produce more positions than ceil(in / s) when the padded extent allows: keep the first oh x ow grid
+    L_h = (H + th - k) // s + 1
+    L_w = (W + tw - k) // s + 1
+    u = u.reshape(2, L_h, L_w, k * k * 3)[:, :oh, :ow]
+    assert got.shape == (2, oh, ow, k * k * 3)
+    np.testing.assert_array_equal(got, u.numpy())
+    np.testing.assert_array_equal(got, spec_numpy.extract_patches_same(x, k, s))
+
+
+def test_shim_keras_training_plumbing():
+    """`training` resolution of Layer.__call__: explicit > enclosing call > the layer's own `call` default; Sequential forwards
+    it to layers whose `call` names it (keras Sequential.call).  The reference relies on all three (vit.py:21,159-175)."""
+    with tf_shim.installed():
+        from tensorflow.keras import Sequential
+        from tensorflow.keras.layers import Layer
+        import tensorflow.keras.layers as nn
+        seen = []
+
+        class Probe(Layer):
+            def call(self, x, training=True):
+                seen.append(training)
+                return x
+
+        class NoArg(Layer):
+            def call(self, x):
+                return x
+
+        class Outer(Layer):
+            def __init__(self):
+                super().__init__()
+                self.inner = Sequential([Probe(), NoArg(), nn.Dropout(rate=0.5)])
+
+            def call(self, x, training=True):
+                return self.inner(x)                 # no explicit training: inherited from this call
+
+        x = np.ones((4, 8), np.float32)
+        o = Outer()
+        assert np.array_equal(o(x, training=False), x) and seen == [False]
+        y = o(x, training=True)
+        assert seen == [False, True] and set(np.unique(y)) <= {0.0, 2.0} and (y == 0).any()
+        o(x)                                         # nothing given anywhere: call-signature default (True)
+        assert seen[-1] is True
+        Probe()(x, training=False)
+        assert seen[-1] is False
+
+
+def test_shim_leaves_no_fake_tensorflow_behind():
+    before = {n: sys.modules.get(n) for n in ("tensorflow", "tensorflow.keras", "einops.layers.tensorflow", "vit", "t2t")}
+    with tf_shim.installed():
+        import tensorflow as tf
+        assert tf.__version__.endswith("numpy-shim")
+    assert {n: sys.modules.get(n) for n in before} == before
+
+
+# ------------------------------------------------------------------------------------------ 2. live: the reference's code
+def _reference_logits(case, w, img, dtype=np.float64):
+    kind, kw = ref_bind.ctor_kwargs(case)
+    with tf_shim.installed(REF_DIR):
+        model = ref_bind.build_model(kind, kw, {k: v.astype(dtype) for k, v in w.items()}, img.astype(dtype))
+        return ref_bind.to_numpy(model(img.astype(dtype), training=False))
+
+
+@live
+@pytest.mark.parametrize("gen", ["init_weights", "stress_weights"])
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_live_reference_equals_oracle(f64, name, gen):
+    case = SMALL[name]
+    cfg = oracle.make_config(case["kind"], **{k: v for k, v in case.items() if k != "kind"})
+    w = getattr(oracle, gen)(cfg, 21)
+    img = oracle.make_image(cfg, 3, 22)
+    got = _reference_logits(case, w, img)
+    ref = oracle.forward_numpy(img, w, cfg)
+    assert got.dtype == np.float64 and got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ref_torch.forward(img, w, cfg), got, rtol=0, atol=5e-5)
+
+
+@live
+def test_live_reference_smaller_image_and_tokens_entry(f64):
+    """vit.py:165 `pos_embedding[:, :(n + 1)]` on a smaller image, and `model.transformer(tokens)` at arbitrary n (what
+    mae.py:69 / simmim.py:116 call) -- through the reference's own Transformer.call."""
+    case = SMALL["vit_small"]
+    cfg = oracle.make_config("vit", **{k: v for k, v in case.items() if k != "kind"})
+    w = oracle.stress_weights(cfg, 1)
+    w64 = {k: v.astype(np.float64) for k, v in w.items()}
+    img = oracle.make_image(cfg, 2, 3, h=32, w=48).astype(np.float64)
+    kind, kw = ref_bind.ctor_kwargs(case)
+    x = np.random.default_rng(0).standard_normal((3, 9, cfg["dim"]))
+    with tf_shim.installed(REF_DIR):
+        model = ref_bind.build_model(kind, kw, w64, oracle.make_image(cfg, 1, 0).astype(np.float64))
+        got = ref_bind.to_numpy(model(img, training=False))
+        tok = ref_bind.to_numpy(model.transformer(x, training=False))
+        pos = ref_bind.to_numpy(model.pos_embedding[:, 1:5])           # the wrappers' slicing of the attribute (mae.py:54)
+    np.testing.assert_allclose(got, oracle.forward_numpy(img, w, cfg), atol=1e-12)
+    np.testing.assert_allclose(tok, spec_numpy.transformer_tokens(x, w, cfg), atol=1e-12)
+    np.testing.assert_array_equal(pos, w64["pos_embedding"][:, 1:5])
+
+
+@live
+@pytest.mark.parametrize("pool", ["cls", "mean"])
+def test_live_reference_distillable_vit(f64, pool):
+    """distill.py:16-45 (DistillMixin.call) through the reference's DistillableViT."""
+    case = dict(SMALL["vit_small"], pool=pool)
+    cfg = oracle.make_config("vit", **{k: v for k, v in case.items() if k != "kind"})
+    w = oracle.stress_weights(cfg, 4)
+    img = oracle.make_image(cfg, 2, 5).astype(np.float64)
+    tok = np.random.default_rng(6).standard_normal((1, 1, cfg["dim"]))
+    kind, kw = ref_bind.ctor_kwargs(case)
+    with tf_shim.installed(REF_DIR):
+        import distill
+        model = ref_bind.build_model("vit", kw, {k: v.astype(np.float64) for k, v in w.items()}, img, cls=distill.DistillableViT)
+        logits, dist = model(img, distill_token=tok, training=False)
+        plain = ref_bind.to_numpy(model(img, training=False))
+    ref_l, ref_d = spec_numpy.forward_distill(img, tok, w, cfg)
+    np.testing.assert_allclose(ref_bind.to_numpy(logits), ref_l, atol=1e-12)
+    np.testing.assert_allclose(ref_bind.to_numpy(dist), ref_d, atol=1e-12)
+    np.testing.assert_allclose(plain, oracle.forward_numpy(img, w, cfg), atol=1e-12)
+
+
+@live
+def test_live_reference_efficient_vit_shell(f64):
+    """efficient.py:12-55 with the reference's own vit.Transformer injected: same logits as vit.ViT on the same weights."""
+    case = SMALL["vit_small"]
+    cfg = oracle.make_config("vit", **{k: v for k, v in case.items() if k != "kind"})
+    w = oracle.stress_weights(cfg, 7)
+    img = oracle.make_image(cfg, 2, 8).astype(np.float64)
+    with tf_shim.installed(REF_DIR):
+        import efficient
+        import vit
+        tr = vit.Transformer(cfg["dim"], cfg["depth"], cfg["heads"], cfg["dim_head"], cfg["mlp_dim"])
+        kw = dict(image_size=case["image_size"], patch_size=case["patch_size"], num_classes=case["num_classes"], dim=case["dim"], transformer=tr)
+        model = ref_bind.build_model("vit", kw, {k: v.astype(np.float64) for k, v in w.items()}, img, cls=efficient.ViT)
+        got = ref_bind.to_numpy(model(img, training=False))
+    np.testing.assert_allclose(got, oracle.forward_numpy(img, w, cfg), atol=1e-12)
+
+
+@live
+def test_live_reference_dropout_is_identity_at_inference_and_random_in_training():
+    """with dropout > 0 the reference's `training=False` forward equals the dropout-free one; `training=True`
+    (the signature default, vit.py:159) differs."""
+    case = dict(SMALL["vit_small"], dropout=0.3, emb_dropout=0.2)
+    cfg = oracle.make_config("vit", **{k: v for k, v in SMALL["vit_small"].items() if k != "kind"})
+    w = oracle.stress_weights(cfg, 9)
+    img = oracle.make_image(cfg, 2, 10)
+    kind, kw = ref_bind.ctor_kwargs(case)
+    with tf_shim.installed(REF_DIR):
+        model = ref_bind.build_model(kind, kw, w, img)
+        inf = ref_bind.to_numpy(model(img, training=False))
+        trn = ref_bind.to_numpy(model(img))
+    np.testing.assert_allclose(inf, oracle.forward_numpy(img, w, cfg), atol=2e-5)
+    assert np.abs(trn - inf).max() > 1e-2
+
+
+# ------------------------------------------------------------------------------------------ 3. committed fixtures
+def _fixture(path):
+    z = np.load(path)
+    meta = json.loads(str(z["meta"]))
+    case = meta["config"]
+    for k in ("image_size", "patch_size", "t2t_layers"):            # json turned tuples into lists
+        if isinstance(case.get(k), list):
+            case[k] = tuple(tuple(e) if isinstance(e, list) else e for e in case[k])
+    cfg = oracle.make_config(case["kind"], **{k: v for k, v in case.items() if k != "kind"})
+    w = getattr(oracle, meta["weights"])(cfg, meta["weight_seed"])
+    img = oracle.make_image(cfg, meta["batch"], meta["image_seed"])
+    return z, cfg, w, img
+
+
+def test_every_case_has_a_reference_fixture():
+    have = {os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*__refshim.npz"))}
+    want = {f"{n}__{g}__refshim.npz" for n in list(SMALL) + list(FULL) for g in ("init_weights", "stress_weights")}
+    assert want <= have, sorted(want - have)
+
+
+@pytest.mark.parametrize("gen", ["init_weights", "stress_weights"])
+@pytest.mark.parametrize("name", sorted(SMALL))
+def test_reference_fixture_equals_oracle_small(name, gen):
+    z, cfg, w, img = _fixture(os.path.join(GOLDEN, f"{name}__{gen}__refshim.npz"))
+    ref = oracle.forward_numpy(img, w, cfg)
+    np.testing.assert_allclose(z["logits_ref_f64"], ref, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(z["logits_ref_f32"], ref, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(np.load(os.path.join(GOLDEN, f"{name}__{gen}.npz"))["logits_f64"], z["logits_ref_f64"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("gen", ["init_weights", "stress_weights"])
+@pytest.mark.parametrize("name", sorted(FULL))
+def test_reference_fixture_equals_oracle_at_config_size(name, gen):
+    """BASELINE.json configs[1..4] at their own width / depth / heads, batch 2: the reference's code (float32) against the
+    torch-CPU restatement the GPU config-size test uses as its checker."""
+    z, cfg, w, img = _fixture(os.path.join(GOLDEN, f"{name}__{gen}__refshim.npz"))
+    ref = ref_torch.forward(img, w, cfg)
+    assert z["logits_ref_f32"].shape == ref.shape == (2, 1000)
+    np.testing.assert_allclose(z["logits_ref_f32"], ref, rtol=0, atol=5e-5)
