@@ -275,3 +275,71 @@ def test_reference_fixture_equals_oracle_at_config_size(name, gen):
     ref = ref_torch.forward(img, w, cfg)
     assert z["logits_ref_f32"].shape == ref.shape == (2, 1000)
     np.testing.assert_allclose(z["logits_ref_f32"], ref, rtol=0, atol=5e-5)
+
+
+# ------------------------------------------------------------------------------------------ 4. the boundary
+_PAIRS = [("ViT", "vit", "ViT"), ("DeepViT", "deepvit", "DeepViT"), ("CaiT", "cait", "CaiT"), ("CrossViT", "cross_vit", "CrossViT"),
+          ("ParallelViT", "parallel_vit", "ViT"), ("T2TViT", "t2t", "T2TViT"), ("PatchMergerViT", "vit_with_patch_merger", "ViT"),
+          ("EfficientViT", "efficient", "ViT"), ("PatchMerger", "vit_with_patch_merger", "PatchMerger")]
+
+
+@live
+@pytest.mark.parametrize("ours,mod,theirs", _PAIRS)
+def test_live_constructor_signature_equals_the_reference(ours, mod, theirs):
+    """The drop-in boundary is the constructor + call surface: every positional-or-keyword parameter of the
+    reference's `__init__` -- name, position, default -- is one of ours; what we add (precision / device / seed) is keyword-only."""
+    import importlib
+    import inspect
+    import vit_tensorflow_b200 as vb
+    with tf_shim.installed(REF_DIR):
+        ref_params = list(inspect.signature(getattr(importlib.import_module(mod), theirs).__init__).parameters.values())[1:]
+    our_params = list(inspect.signature(getattr(vb, ours).__init__).parameters.values())[1:]
+    pos = [p for p in our_params if p.kind is inspect.Parameter.POSITIONAL_OR_KEYWORD]
+    assert [(p.name, p.default) for p in pos] == [(p.name, p.default) for p in ref_params]
+    extra = [p for p in our_params if p.kind is not inspect.Parameter.POSITIONAL_OR_KEYWORD]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in extra) and {p.name for p in extra} <= {"precision", "device", "seed"}
+
+
+@live
+@pytest.mark.parametrize("ours,mod,theirs,kw", [
+    ("ViT", "vit", "ViT", dict(image_size=30, patch_size=16, num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32)),
+    ("ViT", "vit", "ViT", dict(image_size=32, patch_size=16, num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32, pool="max")),
+    ("ViT", "vit", "ViT", dict(image_size=(32, 40), patch_size=(16, 16), num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32)),
+    ("DeepViT", "deepvit", "DeepViT", dict(image_size=30, patch_size=16, num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32)),
+    ("DeepViT", "deepvit", "DeepViT", dict(image_size=32, patch_size=16, num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32, pool="sum")),
+    ("CaiT", "cait", "CaiT", dict(image_size=30, patch_size=16, num_classes=4, dim=32, depth=1, cls_depth=1, heads=2, mlp_dim=32)),
+    ("CrossViT", "cross_vit", "CrossViT", dict(image_size=30, num_classes=4, sm_dim=32, lg_dim=32)),
+    ("ParallelViT", "parallel_vit", "ViT", dict(image_size=30, patch_size=16, num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32)),
+    ("T2TViT", "t2t", "T2TViT", dict(image_size=32, num_classes=4, dim=32)),
+    ("T2TViT", "t2t", "T2TViT", dict(image_size=32, num_classes=4, dim=32, depth=1, heads=2, mlp_dim=32, pool="max")),
+    ("PatchMergerViT", "vit_with_patch_merger", "ViT", dict(image_size=30, patch_size=16, num_classes=4, dim=32, depth=2, heads=2, mlp_dim=32)),
+    ("EfficientViT", "efficient", "ViT", dict(image_size=30, patch_size=16, num_classes=4, dim=32, transformer=None)),
+    ("EfficientViT", "efficient", "ViT", dict(image_size=32, patch_size=16, num_classes=4, dim=32, transformer=None, pool="max")),
+])
+def test_live_constructor_errors_equal_the_reference(ours, mod, theirs, kw):
+    """Same error behaviour at the boundary: whatever the reference's constructor raises for these kwargs (type and message), ours
+    raises too -- before any engine call, so this runs without a GPU."""
+    import importlib
+    import vit_tensorflow_b200 as vb
+    with tf_shim.installed(REF_DIR):
+        with pytest.raises(Exception) as ref_exc:
+            getattr(importlib.import_module(mod), theirs)(**kw)
+    with pytest.raises(Exception) as our_exc:
+        getattr(vb, ours)(**kw)
+    assert type(our_exc.value) is type(ref_exc.value) and str(our_exc.value) == str(ref_exc.value)
+
+
+@live
+@pytest.mark.parametrize("ours,mod,theirs", [p for p in _PAIRS] + [("DistillableViT", "distill", "DistillableViT")])
+def test_live_call_signature_equals_the_reference(ours, mod, theirs):
+    """`model(img, training=True, **kwargs)` (vit.py:159): parameter names, order, defaults and the **kwargs catch-all of the
+    reference's `call` are those of our `__call__` (which is also reachable as `.call`, as on a Keras model)."""
+    import importlib
+    import inspect
+    import vit_tensorflow_b200 as vb
+    with tf_shim.installed(REF_DIR):
+        ref = list(inspect.signature(getattr(importlib.import_module(mod), theirs).call).parameters.values())[1:]
+    cls = getattr(vb, ours)
+    mine = list(inspect.signature(cls.__call__).parameters.values())[1:]
+    assert [(p.name, p.kind, p.default) for p in mine] == [(p.name, p.kind, p.default) for p in ref]
+    assert cls.call is cls.__call__ or inspect.signature(cls.call) == inspect.signature(cls.__call__)
