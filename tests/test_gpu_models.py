@@ -165,6 +165,10 @@ def test_patch_embedding_layers(lib, precision):
     assert emb.shape == ref.shape and (np.abs(emb - ref) <= tol).all()
     np.testing.assert_array_equal(m.patch_embedding(img), emb)
     assert m.pos_embedding.shape == (1, cfg["num_patches"] + 1, cfg["dim"]) and m.cls_token.shape == (1, 1, cfg["dim"])
+    # mae.py:38 / simmim.py:80: `pixel_values_per_patch = self.patch_to_emb.weights[0].shape[0]`
+    assert patch_to_emb.weights[0].shape[0] == cfg["patch_h"] * cfg["patch_w"] * 3 and len(patch_to_emb.weights) == 2
+    np.testing.assert_array_equal(patch_to_emb.weights[0], w["patch.kernel"])
+    np.testing.assert_array_equal(patch_to_emb.get_weights()[1], w["patch.bias"])
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])

@@ -59,13 +59,38 @@ class _Layer:
         return self._fn(x)
 
 
+class _DenseLayer(_Layer):
+    """Stands where the reference has an `nn.Dense`: callable, plus the Keras variable list the wrappers read the patch
+    size from -- `patch_to_emb.weights[0].shape[0]` (mae.py:38, simmim.py:80).  `weights` = [kernel [in, units], bias [units]]
+    as read-only views of the arrays the model holds (assign through `set_weights_dict`)."""
+
+    def __init__(self, fn, model, name):
+        super().__init__(fn)
+        self._m, self._name = model, name
+
+    @property
+    def kernel(self):
+        return self._m._weight_view(self._name + ".kernel")
+
+    @property
+    def bias(self):
+        return self._m._weight_view(self._name + ".bias")
+
+    @property
+    def weights(self):
+        return [self.kernel, self.bias]
+
+    def get_weights(self):
+        return [w.copy() for w in self.weights]
+
+
 class _PatchEmbedding(_Layer):
     """`model.patch_embedding` (vit.py:141-144): Sequential([Rearrange, Dense]); the wrappers take `.layers[:2]` apart
     (mae.py:37, simmim.py:79) or call `.layers[-1]` (mpp.py:200)."""
 
     def __init__(self, model):
         super().__init__(model.forward_patch_embedding)
-        self.layers = [_Layer(model.to_patch), _Layer(model.patch_to_emb)]
+        self.layers = [_Layer(model.to_patch), _DenseLayer(model.patch_to_emb, model, "patch")]
 
 
 class _EngineModel:
