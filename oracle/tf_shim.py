@@ -27,6 +27,7 @@ double precision, which turns the comparison with the float64 spec into a ~1e-12
 """
 from __future__ import annotations
 
+import collections
 import contextlib
 import inspect
 import math
@@ -53,7 +54,28 @@ def set_seed(seed: int) -> None:
 
 
 # ------------------------------------------------------------------------------------------------ tensors
-class Variable(np.ndarray):
+class Tensor(np.ndarray):
+    """What tf.* functions and layer calls return: an ndarray (einops and numpy treat it as one) that also answers
+    `.numpy()`, which the reference's wrappers call on results (`encoded.numpy()[batch_range, masked_indices]`, simmim.py:119)."""
+
+    def numpy(self):
+        return self.view(np.ndarray)
+
+
+def _t(x):
+    """ndarray results (and tuples / lists of them) -> Tensor views; everything else unchanged."""
+    if isinstance(x, np.ndarray):
+        return x if isinstance(x, Tensor) else x.view(Tensor)
+    if isinstance(x, (np.generic,)):
+        return np.asarray(x).view(Tensor)
+    if isinstance(x, tuple) and not hasattr(x, "_fields"):
+        return tuple(_t(e) for e in x)
+    if isinstance(x, list):
+        return [_t(e) for e in x]
+    return x
+
+
+class Variable(Tensor):
     """tf.Variable: owns its storage, `.assign` overwrites in place (same shape, as Keras requires)."""
 
     def __new__(cls, initial_value=None, trainable=True, name=None, dtype=None, **_):
@@ -66,10 +88,6 @@ class Variable(np.ndarray):
             raise ValueError(f"Variable.assign: shape {value.shape} does not match {self.shape}")
         np.copyto(self, value.astype(self.dtype))
         return self
-
-    def numpy(self):
-        return np.array(self, copy=True).view(np.ndarray)
-
 
 def _arr(x):
     return x if isinstance(x, np.ndarray) else np.asarray(x, dtype=_DTYPE[0])
@@ -173,20 +191,28 @@ class Layer:
             value = params["training"].default
         if accepts and value is not None:
             kwargs["training"] = value
-        elif "training" in kwargs and kwargs["training"] is None:
-            del kwargs["training"]
+        elif "training" in kwargs and (kwargs["training"] is None or not accepts):
+            del kwargs["training"]       # keras drops a `training` the layer's call does not take (simmim.py:88 passes it to Rearrange)
         _TRAINING_CTX.append(value)
         try:
-            return self.call(*args, **kwargs)
+            return _t(self.call(*args, **kwargs))
         finally:
             _TRAINING_CTX.pop()
 
     def call(self, inputs, *args, **kwargs):
         return inputs
 
+    @property
+    def weights(self):
+        """The layer's own variables in creation order (`patch_to_emb.weights[0].shape[0]`, mae.py:38)."""
+        return [v for v in vars(self).values() if isinstance(v, Variable)]
+
 
 class Model(Layer):
-    pass
+    def build(self, input_shape):
+        """keras.Model.build on a subclassed model runs `call` on a placeholder of `input_shape` so that every sub-layer creates
+        its variables (mae.py:32, simmim.py:74, mpp.py:149)."""
+        self(np.zeros(tuple(input_shape), dtype=_DTYPE[0]))
 
 
 class Sequential(Model):
@@ -304,6 +330,54 @@ class Dropout(Layer):
         return x * keep / (1.0 - self.rate)
 
 
+class Embedding(Layer):
+    """keras.layers.Embedding (mae.py:44): table `[input_dim, output_dim]`, uniform(-0.05, 0.05), built on first call."""
+
+    def __init__(self, input_dim, output_dim, name=None, **kwargs):
+        super().__init__(name=name)
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.embeddings = None
+
+    def call(self, inputs):
+        if self.embeddings is None:
+            self.embeddings = Variable(_RNG[0].uniform(-0.05, 0.05, size=(self.input_dim, self.output_dim)))
+        return self.embeddings.view(np.ndarray)[np.asarray(inputs)]
+
+
+def _top_k(input, k=1, sorted=True, **_):
+    x = _arr(input)
+    idx = np.argsort(-x, axis=-1, kind="stable")[..., :k].astype(np.int32)
+    return _TopKV2(_t(np.take_along_axis(x, idx, axis=-1)), _t(idx))
+
+
+_TopKV2 = collections.namedtuple("TopKV2", ["values", "indices"])
+
+
+def _categorical_crossentropy(y_true, y_pred, from_logits=False, **_):
+    y_true, y_pred = _arr(y_true), _arr(y_pred)
+    logp = _log_softmax(y_pred, -1) if from_logits else np.log(np.clip(y_pred / y_pred.sum(-1, keepdims=True), 1e-7, 1.0))
+    return -(y_true * logp).sum(-1)
+
+
+class _KLDivergence:
+    """keras.losses.KLDivergence: sum(y_true * log(y_true / y_pred)) over the last axis, both clipped to [1e-7, 1]."""
+
+    def __init__(self, reduction="auto", name=None):
+        self.reduction = reduction
+
+    def __call__(self, y_true, y_pred):
+        y_true, y_pred = np.clip(_arr(y_true), 1e-7, 1.0), np.clip(_arr(y_pred), 1e-7, 1.0)
+        per = (y_true * np.log(y_true / y_pred)).sum(-1)
+        return _t(per if self.reduction == "none" else per.mean())
+
+
+def _returns_tensor(f):
+    def wrapped(*a, **k):
+        return _t(f(*a, **k))
+    wrapped.__name__ = getattr(f, "__name__", "op")
+    return wrapped
+
+
 # ------------------------------------------------------------------------------------------------ module objects
 def _module(name, **attrs):
     m = types.ModuleType(name)
@@ -333,15 +407,37 @@ def _build_modules():
         normal=lambda shape, mean=0.0, stddev=1.0, dtype=None, **_: (mean + stddev * _RNG[0].standard_normal(tuple(shape))).astype(dtype or _DTYPE[0]),
         uniform=lambda shape, minval=0, maxval=None, dtype=None, **_: _uniform(shape, minval, maxval, dtype),
     )
-    tf.math = _module("tensorflow.math", erf=_erf_op, tanh=tf.tanh, pow=tf.pow)
-    tf.nn = _module("tensorflow.nn", softmax=_softmax, log_softmax=_log_softmax)
+    tf.math = _module("tensorflow.math", erf=_erf_op, tanh=tf.tanh, pow=tf.pow, top_k=_top_k)
+    tf.nn = _module("tensorflow.nn", softmax=_softmax, log_softmax=_log_softmax,
+                    softmax_cross_entropy_with_logits=lambda labels, logits, axis=-1, **_: -(_arr(labels) * _log_softmax(logits, axis)).sum(axis=axis))
     tf.image = _module("tensorflow.image", extract_patches=_extract_patches)
+    # --- beyond the hot path: what the training-loss wrappers (mae.py, simmim.py, mpp.py, distill.py) call around the encoder.
+    # Present so that those wrappers RUN over a drop-in encoder in tests/test_wrappers_over_dropin.py; no parity claim rests on them.
+    tf.__dict__.update(
+        range=lambda start, limit=None, delta=1, dtype=None, **_: np.arange(*((0, start) if limit is None else (start, limit)), delta, dtype=dtype or np.int32),
+        argsort=lambda values, axis=-1, direction="ASCENDING", **_: (np.argsort(_arr(values) if direction == "ASCENDING" else -_arr(values), axis=axis, kind="stable")).astype(np.int32),
+        square=lambda x, *_, **__: np.square(_arr(x)), abs=lambda x, **_: np.abs(_arr(x)),
+        zeros=lambda shape, dtype=None, **_: np.zeros(tuple(shape), dtype=dtype or _DTYPE[0]),
+        where=lambda condition, x=None, y=None, **_: np.where(_arr(condition), _arr(x), _arr(y)),
+        expand_dims=lambda x, axis, **_: np.expand_dims(_arr(x), axis), reshape=lambda x, shape, **_: np.reshape(_arr(x), tuple(shape)),
+        convert_to_tensor=lambda v, dtype=None, **_: np.asarray(v, dtype=dtype or _DTYPE[0]),
+        clip_by_value=lambda t, clip_value_min, clip_value_max, **_: np.clip(_arr(t), clip_value_min, clip_value_max),
+        reduce_min=lambda x, axis=None, keepdims=False: _arr(x).min(axis=axis, keepdims=keepdims), bool=np.bool_)
+    tf.compat = _module("tensorflow.compat", v1=_module("tensorflow.compat.v1", raw_ops=_module(
+        "tensorflow.compat.v1.raw_ops", Bucketize=lambda input, boundaries, **_: _t(np.digitize(_arr(input), np.asarray(boundaries), right=False).astype(np.int32)))))
+    for mod in (tf, tf.random, tf.math, tf.nn, tf.image):
+        for k, f in list(vars(mod).items()):
+            if isinstance(f, types.FunctionType):
+                setattr(mod, k, _returns_tensor(f))
+    losses = _module("tensorflow.keras.losses", categorical_crossentropy=_returns_tensor(_categorical_crossentropy),
+                     KLDivergence=_KLDivergence, Reduction=types.SimpleNamespace(NONE="none", SUM="sum", AUTO="auto"))
     layers = _module("tensorflow.keras.layers", Layer=Layer, Dense=Dense, LayerNormalization=LayerNormalization,
-                     Softmax=Softmax, Activation=Activation, Dropout=Dropout)
-    keras = _module("tensorflow.keras", __path__=[], Model=Model, Sequential=Sequential, layers=layers)
+                     Softmax=Softmax, Activation=Activation, Dropout=Dropout, Embedding=Embedding)
+    keras = _module("tensorflow.keras", __path__=[], Model=Model, Sequential=Sequential, layers=layers, losses=losses)
     tf.keras = keras
     return {"tensorflow": tf, "tensorflow.random": tf.random, "tensorflow.math": tf.math, "tensorflow.nn": tf.nn,
-            "tensorflow.image": tf.image, "tensorflow.keras": keras, "tensorflow.keras.layers": layers}
+            "tensorflow.image": tf.image, "tensorflow.keras": keras, "tensorflow.keras.layers": layers,
+            "tensorflow.keras.losses": losses}
 
 
 def _uniform(shape, minval, maxval, dtype):
@@ -375,7 +471,8 @@ def _einops_tf_layers():
     return _module("einops.layers.tensorflow", Rearrange=Rearrange, Reduce=Reduce)
 
 
-REFERENCE_MODULES = ("vit", "deepvit", "cait", "cross_vit", "t2t", "parallel_vit", "vit_with_patch_merger", "efficient", "distill")
+REFERENCE_MODULES = ("vit", "deepvit", "cait", "cross_vit", "t2t", "parallel_vit", "vit_with_patch_merger", "efficient", "distill",
+                     "mae", "simmim", "mpp")
 
 
 @contextlib.contextmanager

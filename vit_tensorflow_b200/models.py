@@ -39,6 +39,24 @@ def _layerscale_eps(depth):  # cait.py:36-41
     return 1e-6
 
 
+class _Array(np.ndarray):
+    """What the host classes hand back: a float32 numpy array that also answers `.numpy()`.  The reference's outputs are eager
+    TensorFlow tensors and its wrappers call `.numpy()` on them and on anything derived from them -- `tokens.numpy()[batch_range,
+    unmasked_indices]` (mae.py:63), `encoded.numpy()[batch_range, masked_indices]`, `patches.numpy()` (simmim.py:119,125) -- so a
+    plain ndarray would break those wrappers; arithmetic on an `_Array` yields an `_Array`, so derived values keep the method."""
+
+    def numpy(self):
+        return self.view(np.ndarray)
+
+    def __array_wrap__(self, obj, context=None, return_scalar=False):
+        out = super().__array_wrap__(obj, context, return_scalar)
+        return out[()] if isinstance(out, np.ndarray) and out.ndim == 0 else out    # reductions give numpy scalars, as on ndarray
+
+
+def _as_tensor(a):
+    return a.view(_Array)
+
+
 class _Transformer:
     """`model.transformer(tokens)` (vit.py:99-104): the entry the reference's wrappers call with any n."""
 
@@ -178,7 +196,7 @@ class _EngineModel:
             raise AttributeError(f"{type(self).__name__} has no weight '{name}'")
         a = self._weights[name].view()
         a.flags.writeable = False
-        return a
+        return a.view(_Array)
 
     @property
     def pos_embedding(self):
@@ -219,7 +237,7 @@ class _EngineModel:
         b, h, w, _ = x.shape
         out = np.empty((b, self.num_classes), np.float32)
         self.forward_raw(x.ctypes.data, _lib.MEM_HOST, b, h, w, out.ctypes.data, _lib.MEM_HOST, None)
-        return out
+        return _as_tensor(out)
 
     call = __call__
 
@@ -238,7 +256,7 @@ class _EngineModel:
         out = np.empty_like(x)
         _lib.check(self._lib.vb_forward_tokens(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, n,
                                                out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
-        return out
+        return _as_tensor(out)
 
     # ---- the stages of `call` on their own ------------------------------------------
     def _img(self, img):
@@ -258,7 +276,7 @@ class _EngineModel:
         out = np.empty((b, rows, self._cfg.dim), np.float32)
         _lib.check(self._lib.vb_forward_embed(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, h, w,
                                               out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
-        return out
+        return _as_tensor(out)
 
     def forward_head(self, tokens):
         """`call` after the transformer (vit.py:170-175): pooling + mlp_head; [b, n, dim] (or [b, dim]) -> logits."""
@@ -272,7 +290,7 @@ class _EngineModel:
         out = np.empty((b, self.num_classes), np.float32)
         _lib.check(self._lib.vb_forward_head(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, n,
                                              out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
-        return out
+        return _as_tensor(out)
 
     def to_patch(self, img):
         """`patch_embedding.layers[0]`: Rearrange('b (h p1) (w p2) c -> b (h w) (p1 p2 c)') (vit.py:142)."""
@@ -284,7 +302,7 @@ class _EngineModel:
         out = np.empty((b, (h // ph) * (w // pw), ph * pw * c), np.float32)
         _lib.check(self._lib.vb_to_patch(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, h, w,
                                          out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
-        return out
+        return _as_tensor(out)
 
     def patch_to_emb(self, patches):
         """`patch_embedding.layers[1]`: the Dense(dim) on patch vectors [..., patch_dim] (vit.py:143)."""
@@ -297,7 +315,7 @@ class _EngineModel:
         out = np.empty(x.shape[:-1] + (self._cfg.dim,), np.float32)
         _lib.check(self._lib.vb_patch_to_emb(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, rows,
                                              out.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
-        return out
+        return _as_tensor(out)
 
     def forward_patch_embedding(self, img):
         """`model.patch_embedding(img)` (vit.py:160)."""
@@ -409,7 +427,7 @@ class DistillableViT(ViT):
         _lib.check(self._lib.vb_forward_distill(self._h, x.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, b, h, w,
                                                 tok.ctypes.data_as(C.c_void_p), logits.ctypes.data_as(C.c_void_p),
                                                 dist.ctypes.data_as(C.c_void_p), _lib.MEM_HOST, None), self._h)
-        return logits, dist
+        return _as_tensor(logits), _as_tensor(dist)
 
     call = __call__
 
@@ -547,7 +565,7 @@ class PatchMerger:
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 3 or x.shape[2] != self.dim:
             raise ValueError(f"x must be [b, n, {self.dim}]")
-        return _lib.op_patch_merger(x, self.norm_gamma, self.norm_beta, self.queries, precision=self.precision)[0]
+        return _as_tensor(_lib.op_patch_merger(x, self.norm_gamma, self.norm_beta, self.queries, precision=self.precision)[0])
 
     call = __call__
 
