@@ -5,7 +5,7 @@ product).  What sits between the user and the C-ABI -- kwargs, ctypes marshallin
 poke at (`patch_embedding.layers[:2]`, `.weights`, `pos_embedding[:, 1:n]`, `transformer(tokens)`, `.numpy()` on results) -- is
 plain Python, though, and can be exercised on a CPU box by handing the host classes an object that answers the same `vb_*`
 calls on the same pointers, computing with the oracle.  `installed()` swaps it in for `_lib.load()`; nothing outside tests/ ever
-imports this module.  Kinds: vit, deepvit (what the wrappers take as encoder).
+imports this module.
 """
 import contextlib
 import ctypes as C
@@ -16,7 +16,7 @@ from einops import rearrange
 import oracle
 from oracle import spec_numpy
 
-_KINDS = {0: "vit", 1: "deepvit"}
+_KINDS = {0: "vit", 1: "deepvit", 2: "cait", 3: "crossvit", 4: "parallel_vit", 5: "patch_merger_vit", 6: "t2t_vit"}
 
 
 def _f32(ptr, shape):
@@ -28,6 +28,7 @@ def _f32(ptr, shape):
 class FakeLib:
     def __init__(self):
         self.handles = {}
+        self.next_key = 0
         self.calls = []                # (entry, detail) log: the tests assert on what the host classes asked the engine for
         self.err = b""
 
@@ -35,18 +36,43 @@ class FakeLib:
     def vb_abi_version(self):
         return 4
 
+    @staticmethod
+    def _decode(c):
+        """VbConfig (include/vitb200.h) -> oracle config: the inverse of what the host classes' `_create` calls encode."""
+        kind = _KINDS[c.kind]
+        pool = "mean" if c.pool else "cls"
+        common = dict(num_classes=c.num_classes, dim=c.dim, depth=c.depth, heads=c.heads, mlp_dim=c.mlp_dim, dim_head=c.dim_head)
+        if kind in ("vit", "parallel_vit"):
+            extra = dict(num_parallel_branches=c.parallel_branches) if kind == "parallel_vit" else {}
+            return oracle.make_config(kind, image_size=(c.image_h, c.image_w), patch_size=(c.patch_h, c.patch_w), pool=pool, **common, **extra)
+        if kind == "deepvit":
+            return oracle.make_config(kind, image_size=c.image_h, patch_size=c.patch_h, pool=pool, **common)
+        if kind == "cait":
+            return oracle.make_config(kind, image_size=c.image_h, patch_size=c.patch_h, cls_depth=c.cls_depth, **common)
+        if kind == "patch_merger_vit":
+            return oracle.make_config(kind, image_size=(c.image_h, c.image_w), patch_size=(c.patch_h, c.patch_w),
+                                      patch_merge_layer=c.patch_merge_layer_index + 1, patch_merge_num_tokens=c.patch_merge_num_tokens, **common)
+        if kind == "t2t_vit":
+            layers = tuple((getattr(c, f"t2t_k{i}"), getattr(c, f"t2t_s{i}")) for i in range(c.t2t_num_layers))
+            return oracle.make_config(kind, image_size=c.image_h, pool=pool, t2t_layers=layers, **common)
+        if kind == "crossvit":
+            names = ("sm_dim", "lg_dim", "sm_patch_size", "sm_enc_depth", "sm_enc_heads", "sm_enc_mlp_dim", "sm_enc_dim_head", "lg_patch_size",
+                     "lg_enc_depth", "lg_enc_heads", "lg_enc_mlp_dim", "lg_enc_dim_head", "cross_attn_depth", "cross_attn_heads", "cross_attn_dim_head")
+            return oracle.make_config(kind, image_size=c.image_h, num_classes=c.num_classes, depth=c.cross_depth, **{n: getattr(c, n) for n in names})
+        raise ValueError(kind)
+
     def vb_create(self, cfg_ref, device, handle_ref):
         c = cfg_ref._obj
-        if c.kind not in _KINDS:
-            self.err = b"fake engine: kind not supported"
+        if c.kind not in _KINDS or c.struct_size != C.sizeof(type(c)):
+            self.err = b"fake engine: bad config"
             return 1
-        cfg = oracle.make_config(_KINDS[c.kind], image_size=(c.image_h, c.image_w), patch_size=(c.patch_h, c.patch_w),
-                                 num_classes=c.num_classes, dim=c.dim, depth=c.depth, heads=c.heads, mlp_dim=c.mlp_dim,
-                                 dim_head=c.dim_head, pool="mean" if c.pool else "cls") if c.kind == 0 else \
-            oracle.make_config("deepvit", image_size=c.image_h, patch_size=c.patch_h, num_classes=c.num_classes, dim=c.dim, depth=c.depth,
-                               heads=c.heads, mlp_dim=c.mlp_dim, dim_head=c.dim_head, pool="mean" if c.pool else "cls")
-        key = len(self.handles) + 1
-        self.handles[key] = dict(cfg=cfg, specs=list(oracle.weight_specs(cfg).items()), w={}, finalized=False, keep=[])
+        cfg = self._decode(c)
+        specs = list(oracle.weight_specs(cfg).items())
+        if c.depth == 0 and cfg["kind"] == "vit":          # efficient.ViT shell: embed + head only (engine.cu does the same for depth 0)
+            specs = [(n, s) for n, s in specs if not n.startswith("layers.")]
+        self.next_key += 1
+        key = self.next_key
+        self.handles[key] = dict(cfg=cfg, specs=specs, w={}, finalized=False, keep=[])
         handle_ref._obj.value = key
         self.calls.append(("vb_create", cfg["kind"]))
         return 0
@@ -126,7 +152,11 @@ class FakeLib:
 
     def vb_embed_rows(self, h, hh, ww):
         cfg = self._h(h)["cfg"]
-        return (hh // cfg["patch_h"]) * (ww // cfg["patch_w"]) + 1
+        if cfg["kind"] == "t2t_vit":
+            gh, gw = oracle.t2t_token_grid(cfg, hh, ww)[-1]
+            return gh * gw + 1
+        n = (hh // cfg["patch_h"]) * (ww // cfg["patch_w"])
+        return n + (0 if cfg["kind"] in ("cait", "patch_merger_vit") else 1)
 
     def vb_forward_embed(self, h, img, mem_in, b, hh, ww, out, mem_out, stream):
         st = self._ready(h)

@@ -158,3 +158,53 @@ def test_live_distill_wrapper_over_the_dropin_student(hard=False):
             wrapper = distill.DistillWrapper(teacher=teacher, student=student, temperature=3, alpha=0.5, hard=hard)
             out[label] = np.asarray(wrapper([IMG, labels], training=False), dtype=np.float64)
     assert np.isfinite(out["ours"]).all() and np.abs(out["ours"] - out["reference"]).max() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ every host class over the double
+@pytest.mark.parametrize("name", sorted(__import__("cases").SMALL))
+def test_every_host_class_encodes_its_kwargs_losslessly(name):
+    """kwargs -> VbConfig (`_create`) -> engine: decoding the VbConfig the host class built gives back exactly
+    `oracle.make_config(kind, **kwargs)` (so nothing the reference's constructor takes is dropped on the way to the C-ABI), the
+    weight list the engine reports is the oracle's (names, shapes, order) and the forward marshals the right buffers."""
+    from cases import cfg_of
+    from vit_tensorflow_b200 import from_config
+    cfg = cfg_of(name)
+    w = oracle.stress_weights(cfg, 3)
+    img = oracle.make_image(cfg, 2, 4)
+    with fake_engine.installed() as fake:
+        m = from_config(cfg, precision="fp32")
+        assert list(m.weight_specs().items()) == [(k, v[0]) for k, v in oracle.weight_specs(cfg).items()]
+        decoded = fake.handles[m._h.value]["cfg"]
+        raw = ("image_size", "patch_size", "patch_merge_layer")      # int-or-pair / None-or-int spellings of values the derived keys hold
+        assert {k: v for k, v in decoded.items() if k not in raw} == {k: v for k, v in cfg.items() if k not in raw}
+        m.set_weights_dict(w)
+        np.testing.assert_allclose(m(img, training=False), oracle.forward_numpy(img, w, cfg), atol=1e-6)
+        init = m.get_weights_dict()                                       # a fresh model's init follows the reference's distributions
+        m2 = from_config(cfg, precision="fp32", seed=0)
+        for k, v in m2.get_weights_dict().items():
+            leaf = k.rsplit(".", 1)[-1]
+            if leaf in ("bias", "beta"):
+                assert not v.any()
+            elif leaf == "gamma":
+                assert (v == 1).all()
+            elif leaf == "kernel":
+                assert np.abs(v).max() <= np.sqrt(6.0 / sum(v.shape)) + 1e-6
+        assert set(init) == set(m2.get_weights_dict())
+
+
+def test_efficient_vit_and_t2t_with_injected_transformer_over_the_double():
+    """efficient.py:12-55 / t2t.py:84-87: embed -> injected `transformer(tokens, training=...)` -> head, through the stage entries."""
+    from vit_tensorflow_b200 import EfficientViT, T2TViT
+    with fake_engine.installed():
+        enc = _ours()
+        ev = EfficientViT(image_size=64, patch_size=16, num_classes=10, dim=64, transformer=enc.transformer, precision="fp32")
+        ev.set_weights_dict({k: v for k, v in W.items() if not k.startswith("layers.")})
+        np.testing.assert_allclose(ev(IMG, training=False), oracle.forward_numpy(IMG, W, CFG), atol=1e-5)
+        seen = []
+
+        def probe(x, training=True):
+            seen.append((x.shape, training))
+            return x
+        t2 = T2TViT(image_size=32, num_classes=10, dim=64, transformer=probe, t2t_layers=((3, 2), (3, 2)), precision="fp32")
+        out = t2(oracle.make_image(dict(image_h=32, image_w=32, channels=3), 2, 1), training=False)
+        assert out.shape == (2, 10) and seen == [((2, 65, 64), False)]
