@@ -1,6 +1,7 @@
 """Second, independent anchors for the oracle's building blocks: the numpy-float64 spec against PyTorch's own
-implementations of the same published operators, on random inputs.  None of this is TensorFlow (absent from this image: parity stays
-"unpinned" at the Keras boundary), but it is third-party code the spec did not come from:
+implementations of the same published operators, on random inputs.  None of this is TensorFlow (absent from this image: the reference's own
+code is pinned by tests/test_reference_shim.py, the TensorFlow primitives under it stay assumed), but it is
+third-party code the spec did not come from:
 
   attention core (vit.py:77-82)            F.scaled_dot_product_attention
   fused-QKV multi-head attention            torch.nn.MultiheadAttention with mapped weights (vit.py:59,63,72-84)

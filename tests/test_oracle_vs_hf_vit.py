@@ -4,8 +4,8 @@ learned positions on every row, pre-norm blocks with exact-erf GELU, final Layer
 dim_head = dim / heads, qkv_bias = False and layer_norm_eps = 1e-3.  Mapping the oracle's Keras-layout weights into it and
 comparing logits checks the oracle's restatement against code neither written here nor derived from the reference.
 
-This does NOT pin the TensorFlow boundary (Keras' own LayerNormalization / Dense / einops semantics stay as restated in
-SURVEY.md App. A); parity remains "unpinned" in the sense of DESIGN.md section 2."""
+This does NOT pin the TensorFlow boundary (Keras' own LayerNormalization / Dense semantics stay as restated in SURVEY.md App. A
+and oracle/tf_shim.py); the reference's own model code is pinned separately, by running it (tests/test_reference_shim.py)."""
 import numpy as np
 import pytest
 
