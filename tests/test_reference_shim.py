@@ -92,6 +92,21 @@ def test_shim_extract_patches_same_against_torch_unfold(f64, H, W, k, s):
     np.testing.assert_array_equal(got, spec_numpy.extract_patches_same(x, k, s))
 
 
+def test_shim_extract_patches_reproduces_the_tensorflow_api_docs_example():
+    """The worked example of the `tf.image.extract_patches` API documentation: a 10 x 10 image holding 1..100, 3 x 3 patches, stride 5.
+    'VALID' gives the four patches below; with 'SAME' the output grid is ceil(10 / 5) = 2 as well and the total padding
+    max((2 - 1) * 5 + 3 - 10, 0) = 0, so the result is the same -- a known answer for both the patch-vector order (row, column,
+    channel) and the padding rule."""
+    img = np.arange(1, 101, dtype=np.float32).reshape(1, 10, 10, 1)
+    want = np.array([[[[1, 2, 3, 11, 12, 13, 21, 22, 23], [6, 7, 8, 16, 17, 18, 26, 27, 28]],
+                      [[51, 52, 53, 61, 62, 63, 71, 72, 73], [56, 57, 58, 66, 67, 68, 76, 77, 78]]]], np.float32)
+    with tf_shim.installed() as tf:
+        for padding in ("VALID", "SAME"):
+            got = tf.image.extract_patches(images=img, sizes=[1, 3, 3, 1], strides=[1, 5, 5, 1], rates=[1, 1, 1, 1], padding=padding)
+            np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(spec_numpy.extract_patches_same(img, 3, 5), want)
+
+
 def test_shim_keras_training_plumbing():
     """`training` resolution of Layer.__call__: explicit > enclosing call > the layer's own `call` default; Sequential forwards
     it to layers whose `call` names it (keras Sequential.call).  The reference relies on all three (vit.py:21,159-175)."""
