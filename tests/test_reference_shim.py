@@ -27,7 +27,7 @@ from oracle import ref_bind, ref_torch, spec_numpy, tf_shim
 from cases import FULL, SMALL
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
-REF_DIR = "/root/reference/vit_tensorflow"
+REF_DIR = os.environ.get("VB_REFERENCE_DIR", "/root/reference/vit_tensorflow")    # the reference checkout (absent on the GPU box)
 live = pytest.mark.skipif(not os.path.isdir(REF_DIR), reason="reference checkout not present (GPU box): fixtures cover it")
 
 

@@ -20,7 +20,7 @@ import oracle
 import fake_engine
 from oracle import ref_bind, spec_numpy, tf_shim
 
-REF_DIR = "/root/reference/vit_tensorflow"
+REF_DIR = os.environ.get("VB_REFERENCE_DIR", "/root/reference/vit_tensorflow")    # the reference checkout (absent on the GPU box)
 live = pytest.mark.skipif(not os.path.isdir(REF_DIR), reason="reference checkout not present (GPU box)")
 
 KW = dict(image_size=64, patch_size=16, num_classes=10, dim=64, depth=2, heads=4, mlp_dim=128, dim_head=16)
