@@ -64,6 +64,17 @@ FULL = {
     "c5_vit_l16_384": dict(kind="vit", image_size=384, patch_size=16, num_classes=1000, dim=1024, depth=24, heads=16, mlp_dim=4096),
 }
 
+# The reference README's usage examples of the two hot-path model classes BASELINE.json has no configuration for (CrossViT: SURVEY.md 8
+# a14, README.md:327-345; T2TViT: 8 f3, README.md:208-216), at their own size, batch 2 -- the configurations bench.py --config
+# crossvit_readme / t2t_readme time.
+README = {
+    "crossvit_readme": dict(kind="crossvit", image_size=256, num_classes=1000, depth=4, sm_dim=192, sm_patch_size=16, sm_enc_depth=2,
+                            sm_enc_heads=8, sm_enc_mlp_dim=2048, lg_dim=384, lg_patch_size=64, lg_enc_depth=3, lg_enc_heads=8,
+                            lg_enc_mlp_dim=2048, cross_attn_depth=2, cross_attn_heads=8),
+    "t2t_readme": dict(kind="t2t_vit", image_size=224, num_classes=1000, dim=512, depth=5, heads=8, mlp_dim=512,
+                       t2t_layers=((7, 4), (3, 2), (3, 2))),
+}
+
 
 def cfg_of(name):
     d = dict({**SMALL, **MID}[name])

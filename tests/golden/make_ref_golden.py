@@ -3,7 +3,8 @@ stand-in for TensorFlow in oracle/tf_shim.py.
 
     python tests/golden/make_ref_golden.py [--force] [--reference /root/reference]
 
-For every case of tests/cases.py (SMALL) and every BASELINE.json configuration at its own width / depth / heads (batch 2)
+For every case of tests/cases.py (SMALL), every BASELINE.json configuration at its own width / depth / heads (FULL, batch 2) and the
+reference README's CrossViT / T2TViT usage examples at their own size (README, batch 2)
 this instantiates the reference class (vit.ViT, deepvit.DeepViT, cait.CaiT, cross_vit.CrossViT, parallel_vit.ViT,
 vit_with_patch_merger.ViT, t2t.T2TViT), loads the oracle's seeded weights into its Keras variables by attribute path
 (oracle/ref_bind.py), calls `model(img, training=False)` and stores the logits:
@@ -27,7 +28,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 sys.path.insert(0, os.path.dirname(HERE))
 import oracle  # noqa: E402
 from oracle import ref_bind, tf_shim  # noqa: E402
-from cases import SMALL, FULL  # noqa: E402
+from cases import SMALL, FULL, README  # noqa: E402
 
 WEIGHT_SEED, IMAGE_SEED, BATCH = 11, 12, 2
 
@@ -51,7 +52,7 @@ def main():
     ref_dir = os.path.join(ref_root, "vit_tensorflow")
     if not os.path.isdir(ref_dir):
         raise SystemExit(f"{ref_dir} not found: these fixtures can only be generated where the reference checkout exists")
-    for group, cases in (("small", SMALL), ("full", FULL)):
+    for group, cases in (("small", SMALL), ("full", FULL), ("readme", README)):
         for name, case in cases.items():
             for wname in ("init_weights", "stress_weights"):
                 path = os.path.join(HERE, f"{name}__{wname}__refshim.npz")

@@ -15,18 +15,22 @@ import pytest
 
 import oracle
 from oracle import ref_torch
-from cases import FULL  # BASELINE.json configs[1..4] at batch 2
+from cases import FULL, README  # BASELINE.json configs[1..4] and the README's CrossViT / T2TViT examples, at batch 2
 
 pytestmark = pytest.mark.gpu
 
 # |err| <= ATOL + RTOL * |ref| on logits of standard deviation ~1 (|ref| max 2.6 - 4.3).  Measured maxima on the B200 are in
 # the comment of each line; the bound is <= 3x that.
+CROSSVIT_README_TOL = (1.2e-1, 4.0e-2)      # provisional until measured on the B200
+T2T_README_TOL = (1.2e-1, 4.0e-2)           # provisional until measured on the B200
 TOL = {   # (atol, rtol); measured max |err| on the B200, round 2 (gpurun_out/config_size_parity.json -> DESIGN.md section 6):
     "c2_vit_b16_224": (4.0e-2, 1.0e-2),        # 0.026 (stress) / 0.030 (init), |ref| <= 3.9
     "c3_deepvit_1024x24": (6.0e-2, 2.0e-2),    # 0.038 / 0.044, |ref| <= 3.7
     "c4_cait_s36_dh48": (7.0e-2, 2.0e-2),      # 0.050 / 0.023 (38 layers, O(1) LayerScale in the stress set), |ref| <= 2.8
     "c4_cait_s36_dh64": (9.0e-2, 2.0e-2),      # 0.072 / 0.022 (fused mix kernel; 0.042 with the round-1 three-kernel path)
     "c5_vit_l16_384": (6.0e-2, 1.5e-2),        # 0.036 / 0.041, |ref| <= 4.3
+    "crossvit_readme": CROSSVIT_README_TOL,
+    "t2t_readme": T2T_README_TOL,
 }
 
 
@@ -45,10 +49,10 @@ def _record(name, gen, rec):
 
 
 @pytest.mark.parametrize("gen", ["stress_weights", "init_weights"])
-@pytest.mark.parametrize("name", sorted(FULL))
+@pytest.mark.parametrize("name", sorted(FULL) + sorted(README))
 def test_bf16_vs_oracle_at_config_size(lib, name, gen):
     from vit_tensorflow_b200 import from_config
-    c = dict(FULL[name])
+    c = dict({**FULL, **README}[name])
     cfg = oracle.make_config(c.pop("kind"), **c)
     w = getattr(oracle, gen)(cfg, 11)
     img = oracle.make_image(cfg, 2, 12)

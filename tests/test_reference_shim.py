@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 import oracle
 from oracle import ref_bind, ref_torch, spec_numpy, tf_shim
-from cases import FULL, SMALL
+from cases import FULL, README, SMALL
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 REF_DIR = os.environ.get("VB_REFERENCE_DIR", "/root/reference/vit_tensorflow")    # the reference checkout (absent on the GPU box)
@@ -267,7 +267,7 @@ def _fixture(path):
 
 def test_every_case_has_a_reference_fixture():
     have = {os.path.basename(p) for p in glob.glob(os.path.join(GOLDEN, "*__refshim.npz"))}
-    want = {f"{n}__{g}__refshim.npz" for n in list(SMALL) + list(FULL) for g in ("init_weights", "stress_weights")}
+    want = {f"{n}__{g}__refshim.npz" for n in list(SMALL) + list(FULL) + list(README) for g in ("init_weights", "stress_weights")}
     assert want <= have, sorted(want - have)
 
 
@@ -282,10 +282,10 @@ def test_reference_fixture_equals_oracle_small(name, gen):
 
 
 @pytest.mark.parametrize("gen", ["init_weights", "stress_weights"])
-@pytest.mark.parametrize("name", sorted(FULL))
+@pytest.mark.parametrize("name", sorted(FULL) + sorted(README))
 def test_reference_fixture_equals_oracle_at_config_size(name, gen):
-    """BASELINE.json configs[1..4] at their own width / depth / heads, batch 2: the reference's code (float32) against the
-    torch-CPU restatement the GPU config-size test uses as its checker."""
+    """BASELINE.json configs[1..4] at their own width / depth / heads and the README's CrossViT / T2TViT examples at theirs, batch 2:
+    the reference's code (float32) against the torch-CPU restatement the GPU config-size test uses as its checker."""
     z, cfg, w, img = _fixture(os.path.join(GOLDEN, f"{name}__{gen}__refshim.npz"))
     ref = ref_torch.forward(img, w, cfg)
     assert z["logits_ref_f32"].shape == ref.shape == (2, 1000)
